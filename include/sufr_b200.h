@@ -1,0 +1,170 @@
+/*
+ * sufr_b200.h -- C ABI of the B200-native suffix-array / LCP-array constructor.
+ *
+ * Drop-in boundary for ONE path of TravisWheelerLab/sufr (v0.7.12): libsufr's `create`
+ * (`SufrBuilder::<T>::new`, libsufr/src/sufr_builder.rs:143-220, called from
+ * `SuffixArray::write`, libsufr/src/suffix_array.rs:460-470, and `sufr::create`,
+ * sufr/src/lib.rs:321-371).  Everything here is plain C: pointers, sizes, no CUDA or torch types.
+ * A Rust host binds these symbols from an `extern "C"` block (INTEGRATION.md shows the shim).
+ *
+ * Results are bit-exact with the reference for the SA and LCP arrays, u32 and u64 index widths
+ * (see DESIGN.md for the two cases where the reference itself is not a function of its input).
+ * There is no CPU fallback: every entry point that computes fails with an error when no CUDA
+ * device is available.
+ */
+#ifndef SUFR_B200_H
+#define SUFR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUFR_B200_ABI_VERSION 1
+
+/* Return codes. */
+#define SUFR_B200_OK 0
+#define SUFR_B200_ERR_ARGUMENT 1      /* the reference's `bail!` argument errors, same message text */
+#define SUFR_B200_ERR_OUT_OF_MEMORY 2
+#define SUFR_B200_ERR_INTERNAL 3
+#define SUFR_B200_ERR_IO 4            /* "{filename}: {io error}" (sufr_builder.rs:820) */
+#define SUFR_B200_ERR_UNSUPPORTED 5
+#define SUFR_B200_ERR_CUDA 100        /* 100 + cudaError_t */
+
+/* Where a buffer lives. */
+#define SUFR_B200_MEM_HOST 0
+#define SUFR_B200_MEM_DEVICE 1
+
+/* Per-device context: one CUDA stream and one device memory pool.  One context per GPU per process. */
+typedef struct SufrB200Ctx SufrB200Ctx;
+
+/*
+ * Mirrors `SufrBuilderArgs` (libsufr/src/types.rs:527-582) field by field.  Options become a
+ * presence flag + value (max_query_len) or a nullable pointer (path, seed_mask).
+ */
+typedef struct SufrB200Args {
+    const uint8_t* text;          /* types.rs:530  raw text bytes; borrowed for the call */
+    uint64_t text_len;
+    const char* path;             /* types.rs:533  NULL = None ("out.sufr" when a file is written) */
+    uint8_t low_memory;           /* types.rs:536  accepted and ignored, like the reference builder */
+    uint8_t has_max_query_len;    /* types.rs:540  Option tag */
+    uint8_t is_dna;               /* types.rs:546 */
+    uint8_t allow_ambiguity;      /* types.rs:550 */
+    uint8_t ignore_softmask;      /* types.rs:554 */
+    uint8_t reserved[3];
+    uint64_t max_query_len;
+    const uint64_t* sequence_starts;   /* types.rs:558 */
+    const char* const* sequence_names; /* types.rs:562  num_sequences NUL-terminated UTF-8 strings */
+    uint64_t num_sequences;
+    uint64_t num_partitions;      /* types.rs:573  accepted; does not change the result */
+    const char* seed_mask;        /* types.rs:577  NULL = None, else "1101..." */
+    uint64_t random_seed;         /* types.rs:581  accepted; does not change the result */
+    /* Sharding, one process per GPU: this call builds key-range shard `rank` of `world_size`.
+     * Single GPU: rank 0, world_size 1. */
+    int32_t rank;
+    int32_t world_size;
+} SufrB200Args;
+
+/* Phase timings measured with CUDA events on the context's stream (milliseconds). */
+typedef struct SufrB200Timings {
+    double h2d_ms;        /* host -> device copy of the text (0 when the text was already resident) */
+    double encode_ms;     /* text transform, alphabet, packing, N-run scan   (sufr_builder.rs:144-195) */
+    double keys_ms;       /* first key word of every suffix + shard selection (partition assignment, :404-487) */
+    double sort_ms;       /* radix sort of (key, position)                    (sort, :495-598) */
+    double refine_ms;     /* equal-key groups: next-word / prefix-doubling refinement (merge compares, :634-767) */
+    double lcp_ms;        /* LCP values not already produced by the sort      (find_lcp, :268-334) */
+    double finish_ms;     /* N-run tie rule, suffix filter, widening          (:446-449, :305-307) */
+    double d2h_ms;        /* device -> host copy of text / SA / LCP (0 for device results) */
+    double total_ms;      /* first kernel to last kernel, excluding h2d/d2h */
+} SufrB200Timings;
+
+typedef struct SufrB200Result {
+    uint32_t index_bits;      /* 32 or 64: width of the SA / LCP elements */
+    uint32_t memory;          /* SUFR_B200_MEM_HOST (pinned) or SUFR_B200_MEM_DEVICE */
+    uint64_t text_len;
+    uint64_t num_suffixes;    /* suffixes in THIS shard (== total_suffixes when world_size == 1) */
+    uint64_t total_suffixes;  /* SufrBuilder.num_suffixes over all shards */
+    uint64_t shard_offset;    /* rank of this shard's first suffix in the whole suffix array */
+    uint64_t first_suffix;    /* SA[0] / SA[num_suffixes-1] of this shard: inputs of the seam repair */
+    uint64_t last_suffix;     /*   (sufr_builder.rs:893-902); undefined when num_suffixes == 0 */
+    uint8_t* text;            /* transformed text (SufrBuilder.text), text_len bytes */
+    void* sa;                 /* num_suffixes elements of index_bits */
+    void* lcp;                /* num_suffixes elements; lcp[0] of shard > 0 needs sufr_b200_patch_seam */
+    uint64_t* n_ranges;       /* host: num_n_ranges pairs [start, end) (SufrBuilder.n_ranges) */
+    uint64_t num_n_ranges;
+    SufrB200Timings timings;
+    uint64_t kernel_launches; /* kernels launched by this build */
+    uint64_t peak_device_bytes;
+    uint32_t alphabet_size;   /* distinct bytes in the transformed text */
+    uint32_t bits_per_symbol;
+    uint32_t refine_rounds;   /* next-word refinement rounds */
+    uint32_t doubling_rounds; /* prefix-doubling rounds (0 unless the text has deep repeats) */
+    void* owner;              /* internal */
+} SufrB200Result;
+
+/* -- context ------------------------------------------------------------------------------- */
+int sufr_b200_ctx_create(int device, SufrB200Ctx** out);
+void sufr_b200_ctx_destroy(SufrB200Ctx* ctx);
+/* Pre-size the device memory pool for texts of up to `text_len` bytes (optional). */
+int sufr_b200_ctx_reserve(SufrB200Ctx* ctx, uint64_t text_len, uint32_t index_bits);
+/* Give pooled device memory that holds no live result back to the driver. */
+void sufr_b200_ctx_trim(SufrB200Ctx* ctx);
+
+/* -- build: replaces SufrBuilder::<u32>::new / SufrBuilder::<u64>::new up to (not including) write()
+ *    (sufr_builder.rs:143-217).  `text_memory` says where args->text lives, `result_memory` where the
+ *    outputs should be left.  index_bits: 32, 64, or 0 = the reference's dispatch
+ *    (u32 iff text_len < u32::MAX, suffix_array.rs:460-470). */
+int sufr_b200_build(SufrB200Ctx* ctx, const SufrB200Args* args, uint32_t index_bits, int text_memory,
+                    int result_memory, SufrB200Result* out);
+void sufr_b200_result_free(SufrB200Ctx* ctx, SufrB200Result* result);
+
+/* Seam repair between shards (sufr_builder.rs:893-902): sets lcp[0] of this shard to the LCP of
+ * (`prev_last_suffix`, first_suffix).  No-op for an empty shard. */
+int sufr_b200_patch_seam(SufrB200Ctx* ctx, const SufrB200Args* args, SufrB200Result* result,
+                         uint64_t prev_last_suffix);
+
+/* -- write: replaces SufrBuilder::write (sufr_builder.rs:817-918), version-6 `.sufr` layout.
+ *    Single shard: writes the whole file.  Sharded: every rank calls it with the same path; rank 0
+ *    writes header, text and the names tail, every rank pwrites its SA / LCP slice at its offset.
+ *    `result` must be a HOST result. */
+int sufr_b200_write(const SufrB200Args* args, const SufrB200Result* result);
+
+/* -- create: SufrBuilder::new as a single call (build on `device`, then write args->path or
+ *    "out.sufr").  The result is returned like the reference returns the builder struct;
+ *    free it with sufr_b200_result_free(NULL, out).  `out` may be NULL. */
+int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out);
+
+/* -- helpers shared with the host-side mirror ---------------------------------------------- */
+/* SeedMask::new (types.rs:80-97): returns the weight, or -1 if the mask is invalid.
+ * bytes/positions/differences may be NULL; otherwise they need strlen(mask) entries. */
+int64_t sufr_b200_seed_mask(const char* mask, uint8_t* bytes, uint64_t* positions, uint64_t* differences);
+/* find_lcp_full_offset (util.rs:19-37); mask == NULL means "not a mask sort". */
+uint64_t sufr_b200_find_lcp_full_offset(uint64_t lcp, const char* mask);
+
+/* read_sequence_file (util.rs:51-89): FASTA / FASTQ -> text with delimiters and trailing '$'. */
+typedef struct SufrB200Sequences {
+    uint8_t* seq;
+    uint64_t seq_len;
+    uint64_t* start_positions;
+    char** sequence_names;
+    uint64_t num_sequences;
+} SufrB200Sequences;
+int sufr_b200_read_sequence_file(const char* path, uint8_t sequence_delimiter, SufrB200Sequences* out);
+void sufr_b200_sequences_free(SufrB200Sequences* seqs);
+
+/* Synthetic workload generators used by bench.py (device buffers, deterministic in `seed`). */
+int sufr_b200_synth_dna(SufrB200Ctx* ctx, uint8_t* device_text, uint64_t text_len, uint64_t seed,
+                        const uint64_t* record_starts, uint64_t num_records, uint8_t delimiter);
+
+/* Message of the last error on the calling thread. */
+const char* sufr_b200_last_error(void);
+int sufr_b200_abi_version(void);
+/* Number of CUDA devices visible (0 when there is none or the driver is missing). */
+int sufr_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUFR_B200_H */

@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference's `create` interface, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference:
+
+* :class:`SufrBuilderArgs`  -- libsufr/src/types.rs:527-582
+* :class:`SufrBuilder`      -- libsufr/src/sufr_builder.rs:38-220 (``SufrBuilder::<T>::new`` builds AND
+  writes the file; the public fields of the struct are attributes here)
+* :class:`SuffixArray`      -- ``SuffixArray::write`` u32/u64 dispatch, libsufr/src/suffix_array.rs:460-470
+* :class:`SeedMask`         -- libsufr/src/types.rs:36-200
+* :func:`read_sequence_file`, :func:`find_lcp_full_offset` -- libsufr/src/util.rs:51-89, :19-37
+
+Everything that computes goes through ``libsufr_b200.so`` (CUDA, sm_100a).  Nothing here touches the
+oracle and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST
+
+OUTFILE_VERSION = 6          # types.rs:16
+SENTINEL_CHARACTER = b"$"    # types.rs:20
+
+
+class SufrError(RuntimeError):
+    """anyhow::Error of the reference; ``code`` is the C ABI return code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+def _check(rc: int):
+    if rc != _lib.OK:
+        raise SufrError(rc, _lib.lib().sufr_b200_last_error().decode(errors="replace"))
+
+
+# ------------------------------------------------------------------ types.rs:36-200
+@dataclass
+class SeedMask:
+    mask: str
+    bytes: List[int]
+    positions: List[int]
+    differences: List[int]
+    weight: int
+
+    @staticmethod
+    def new(mask: str) -> "SeedMask":
+        n = max(1, len(mask))
+        b = (C.c_uint8 * n)()
+        p = (C.c_uint64 * n)()
+        d = (C.c_uint64 * n)()
+        w = _lib.lib().sufr_b200_seed_mask(mask.encode(), b, p, d)
+        if w < 0:
+            raise SufrError(_lib.ERR_ARGUMENT, f"Invalid seed mask '{mask}'")  # types.rs:82
+        return SeedMask(mask, list(b)[:len(mask)], list(p)[:w], list(d)[:w], int(w))
+
+    @staticmethod
+    def is_valid(mask: str) -> bool:
+        return _lib.lib().sufr_b200_seed_mask(mask.encode(), None, None, None) >= 0
+
+    def __str__(self):
+        return self.mask
+
+
+def find_lcp_full_offset(lcp: int, seed_mask: Optional[str]) -> int:
+    """util.rs:19-37"""
+    return int(_lib.lib().sufr_b200_find_lcp_full_offset(lcp, seed_mask.encode() if seed_mask else None))
+
+
+# ------------------------------------------------------------------ types.rs:271-282, util.rs:51-89
+@dataclass
+class SequenceFileData:
+    seq: bytes
+    start_positions: List[int]
+    sequence_names: List[str]
+
+
+def read_sequence_file(path, sequence_delimiter: bytes = b"%") -> SequenceFileData:
+    s = _lib.Sequences()
+    _check(_lib.lib().sufr_b200_read_sequence_file(str(path).encode(), sequence_delimiter[0], C.byref(s)))
+    try:
+        seq = C.string_at(s.seq, s.seq_len)
+        starts = [int(s.start_positions[i]) for i in range(s.num_sequences)]
+        names = [s.sequence_names[i].decode() for i in range(s.num_sequences)]
+    finally:
+        _lib.lib().sufr_b200_sequences_free(C.byref(s))
+    return SequenceFileData(seq, starts, names)
+
+
+# ------------------------------------------------------------------ types.rs:527-582
+@dataclass
+class SufrBuilderArgs:
+    text: bytes
+    path: Optional[str] = None
+    low_memory: bool = True
+    max_query_len: Optional[int] = None
+    is_dna: bool = False
+    allow_ambiguity: bool = False
+    ignore_softmask: bool = False
+    sequence_starts: Sequence[int] = (0,)
+    sequence_names: Sequence[str] = ("1",)
+    num_partitions: int = 16
+    seed_mask: Optional[str] = None
+    random_seed: int = 42
+
+
+class _CArgs:
+    """Keeps the ctypes buffers behind a SufrB200Args alive."""
+
+    def __init__(self, a: SufrBuilderArgs, *, text_ptr: Optional[int] = None, text_len: Optional[int] = None,
+                 rank: int = 0, world_size: int = 1):
+        self.c = _lib.Args()
+        if text_ptr is None:
+            self._text = np.frombuffer(a.text, dtype=np.uint8) if len(a.text) else np.zeros(1, np.uint8)
+            self.c.text = self._text.ctypes.data
+            self.c.text_len = len(a.text)
+        else:
+            self.c.text = text_ptr
+            self.c.text_len = text_len
+        self.c.path = a.path.encode() if a.path is not None else None
+        self.c.low_memory = int(a.low_memory)
+        self.c.has_max_query_len = int(a.max_query_len is not None)
+        self.c.max_query_len = int(a.max_query_len or 0)
+        self.c.is_dna = int(a.is_dna)
+        self.c.allow_ambiguity = int(a.allow_ambiguity)
+        self.c.ignore_softmask = int(a.ignore_softmask)
+        self._starts = np.asarray(list(a.sequence_starts), dtype=np.uint64)
+        self.c.sequence_starts = self._starts.ctypes.data if len(self._starts) else None
+        names = [s.encode() for s in a.sequence_names]
+        self._names = (C.c_char_p * max(1, len(names)))(*names)
+        self.c.sequence_names = self._names
+        self.c.num_sequences = len(self._starts)
+        self.c.num_partitions = a.num_partitions
+        self.c.seed_mask = a.seed_mask.encode() if a.seed_mask is not None else None
+        self.c.random_seed = a.random_seed
+        self.c.rank = rank
+        self.c.world_size = world_size
+
+
+class Context:
+    """One CUDA stream + device memory pool (SufrB200Ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(_lib.lib().sufr_b200_ctx_create(device, C.byref(self._h)))
+        self.device = device
+
+    def reserve(self, text_len: int, index_bits: int = 32):
+        _check(_lib.lib().sufr_b200_ctx_reserve(self._h, text_len, index_bits))
+
+    def trim(self):
+        _lib.lib().sufr_b200_ctx_trim(self._h)
+
+    def close(self):
+        if self._h:
+            _lib.lib().sufr_b200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class BuildResult:
+    """Owner of one SufrB200Result (host or device memory)."""
+
+    def __init__(self, ctx: Context, cargs: _CArgs, res: "_lib.Result"):
+        self._ctx, self._cargs, self.c = ctx, cargs, res
+
+    # -- scalars
+    @property
+    def index_bits(self): return int(self.c.index_bits)
+    @property
+    def text_len(self): return int(self.c.text_len)
+    @property
+    def num_suffixes(self): return int(self.c.num_suffixes)
+    @property
+    def total_suffixes(self): return int(self.c.total_suffixes)
+    @property
+    def shard_offset(self): return int(self.c.shard_offset)
+    @property
+    def first_suffix(self): return int(self.c.first_suffix)
+    @property
+    def last_suffix(self): return int(self.c.last_suffix)
+    @property
+    def on_device(self): return self.c.memory == MEM_DEVICE
+    @property
+    def timings(self): return self.c.timings.as_dict()
+    @property
+    def kernel_launches(self): return int(self.c.kernel_launches)
+    @property
+    def n_ranges(self) -> List[Tuple[int, int]]:
+        return [(int(self.c.n_ranges[2 * i]), int(self.c.n_ranges[2 * i + 1])) for i in range(self.c.num_n_ranges)]
+
+    def _np(self, ptr, count, dtype):
+        if self.on_device:
+            raise SufrError(_lib.ERR_ARGUMENT, "result lives in device memory")
+        if count == 0:
+            return np.zeros(0, dtype)
+        ct = {np.uint8: C.c_uint8, np.uint32: C.c_uint32, np.uint64: C.c_uint64}[dtype]
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), (count,))
+
+    @property
+    def dtype(self):
+        return np.uint32 if self.c.index_bits == 32 else np.uint64
+
+    @property
+    def text(self) -> bytes:
+        return self._np(self.c.text, self.text_len, np.uint8).tobytes()
+
+    @property
+    def sa(self) -> np.ndarray:
+        return self._np(self.c.sa, self.num_suffixes, self.dtype)
+
+    @property
+    def lcp(self) -> np.ndarray:
+        return self._np(self.c.lcp, self.num_suffixes, self.dtype)
+
+    def _tensor(self, ptr, count, typestr):
+        """Zero-copy torch view of a device buffer (valid until free())."""
+        import torch
+
+        class _Dev:
+            pass
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (max(count, 0),), "typestr": typestr, "data": (int(ptr), False),
+                                      "version": 2}
+        if count == 0:
+            return torch.zeros(0, dtype=torch.int64, device=f"cuda:{self._ctx.device}")
+        return torch.as_tensor(d, device=f"cuda:{self._ctx.device}")
+
+    def sa_tensor(self):
+        """Device result: the suffix array as an int32 / int64 torch tensor (same bits as u32 / u64)."""
+        return self._tensor(self.c.sa, self.num_suffixes, "<i4" if self.c.index_bits == 32 else "<i8")
+
+    def lcp_tensor(self):
+        return self._tensor(self.c.lcp, self.num_suffixes, "<i4" if self.c.index_bits == 32 else "<i8")
+
+    def text_tensor(self):
+        return self._tensor(self.c.text, self.text_len, "|u1")
+
+    def device_pointers(self):
+        """(text, sa, lcp) raw device addresses of a device result."""
+        return int(self.c.text or 0), int(self.c.sa or 0), int(self.c.lcp or 0)
+
+    def patch_seam(self, prev_last_suffix: int):
+        _check(_lib.lib().sufr_b200_patch_seam(self._ctx.handle, C.byref(self._cargs.c), C.byref(self.c),
+                                               prev_last_suffix))
+
+    def write(self):
+        _check(_lib.lib().sufr_b200_write(C.byref(self._cargs.c), C.byref(self.c)))
+
+    def free(self):
+        if self.c.owner:
+            _lib.lib().sufr_b200_result_free(self._ctx.handle, C.byref(self.c))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def build(args: SufrBuilderArgs, *, index_bits: int = 0, ctx: Optional[Context] = None, device: int = 0,
+          result_memory: int = MEM_HOST, device_text: Optional[Tuple[int, int]] = None,
+          rank: int = 0, world_size: int = 1) -> BuildResult:
+    """SufrBuilder::new up to (not including) write(): sufr_b200_build.
+
+    ``device_text=(ptr, len)`` passes a text that already lives in device memory.
+    """
+    ctx = ctx or default_context(device)
+    if device_text is not None:
+        cargs = _CArgs(args, text_ptr=device_text[0], text_len=device_text[1], rank=rank, world_size=world_size)
+        text_memory = MEM_DEVICE
+    else:
+        cargs = _CArgs(args, rank=rank, world_size=world_size)
+        text_memory = MEM_HOST
+    res = _lib.Result()
+    _check(_lib.lib().sufr_b200_build(ctx.handle, C.byref(cargs.c), index_bits, text_memory, result_memory,
+                                      C.byref(res)))
+    return BuildResult(ctx, cargs, res)
+
+
+class SufrBuilder:
+    """``SufrBuilder::<T>::new(args)``: builds the suffix and LCP arrays on the GPU and writes the
+    `.sufr` file at ``args.path`` (default "out.sufr", sufr_builder.rs:215).  ``index_bits`` plays the
+    role of the type parameter T (32 -> u32, 64 -> u64)."""
+
+    def __init__(self, args: SufrBuilderArgs, index_bits: int = 32, *, ctx: Optional[Context] = None,
+                 device: int = 0, write: bool = True):
+        if index_bits not in (32, 64):
+            raise SufrError(_lib.ERR_ARGUMENT, "index_bits must be 32 or 64")
+        self._res = build(args, index_bits=index_bits, ctx=ctx, device=device)
+        r = self._res
+        self.version = OUTFILE_VERSION
+        self.is_dna = args.is_dna
+        self.allow_ambiguity = args.allow_ambiguity
+        self.ignore_softmask = args.ignore_softmask
+        self.text_len = r.text_len
+        self.num_suffixes = r.num_suffixes
+        self.num_sequences = len(args.sequence_starts)
+        self.sequence_starts = list(args.sequence_starts)
+        self.sequence_names = list(args.sequence_names)
+        self.text = r.text
+        self.sort_type = ("Mask", SeedMask.new(args.seed_mask)) if args.seed_mask is not None else \
+            ("MaxQueryLen", args.max_query_len or 0)
+        self.n_ranges = r.n_ranges
+        self.path = args.path if args.path is not None else "out.sufr"
+        self.index_bits = index_bits
+        # not part of the reference struct (its arrays live in temp files): kept for library users
+        self.suffix_array = r.sa
+        self.lcp_array = r.lcp
+        self.timings = r.timings
+        if write:
+            r.write()
+
+
+class SuffixArray:
+    """The write half of libsufr::suffix_array::SuffixArray."""
+
+    @staticmethod
+    def write(args: SufrBuilderArgs, **kw) -> str:
+        # suffix_array.rs:460-470: u32 iff text.len() < u32::MAX
+        bits = 32 if len(args.text) < 0xFFFFFFFF else 64
+        return SufrBuilder(args, bits, **kw).path

@@ -1,0 +1,951 @@
+// Build pipeline + C ABI of libsufr_b200.so.
+//
+// Replaces SufrBuilder::<T>::new up to write() (libsufr/src/sufr_builder.rs:143-217) on one B200:
+//
+//   encode   transform_kernel, pack_kernel            text transform, dense alphabet, packed text
+//   keys     keygen_kernel (or shard compaction)      first key word of every suffix
+//   sort     rsort::{upsweep,scan,downsweep}          stable LSD radix sort of (key word, position)
+//   refine   resolve / active compaction / segmented  groups of equal key words: next key word, then
+//            sort rounds, then prefix doubling        (full sort only) prefix doubling on ranks
+//   lcp      resolve_kernel, lcp_complete_kernel      LCP from clz(x ^ y) of adjacent key words
+//   finish   N-run tie rule, suffix filter, widen     sufr_builder.rs:305-307, :446-449
+//
+// The oracle (oracle/) is never linked or called from here.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sufr_b200.h"
+#include "common.cuh"
+#include "host_io.hpp"
+#include "kernels.cuh"
+#include "keys.cuh"
+#include "pool.hpp"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sufr {
+
+thread_local std::string g_last_error;
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevicePool pool;
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+// Holds everything a returned result owns.
+struct ResultOwner {
+    Ctx* ctx = nullptr;          // device buffers go back to this pool
+    bool owns_ctx = false;       // sufr_b200_create made a private context
+    int memory = SUFR_B200_MEM_HOST;
+    void* text = nullptr;
+    void* sa = nullptr;
+    void* lcp = nullptr;
+    uint64_t* n_ranges = nullptr;
+    // kept for sufr_b200_patch_seam on device results
+};
+
+struct EventTimer {
+    cudaStream_t stream;
+    std::vector<cudaEvent_t> ev;
+    explicit EventTimer(cudaStream_t s) : stream(s) {}
+    ~EventTimer() {
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+    int mark() {
+        cudaEvent_t e;
+        SUFR_CUDA_CHECK(cudaEventCreate(&e));
+        SUFR_CUDA_CHECK(cudaEventRecord(e, stream));
+        ev.push_back(e);
+        return (int)ev.size() - 1;
+    }
+    double ms(int a, int b) {
+        float t = 0;
+        SUFR_CUDA_CHECK(cudaEventElapsedTime(&t, ev[a], ev[b]));
+        return t;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+class Build {
+   public:
+    Build(Ctx& c, const SufrB200Args& a, uint32_t index_bits, int text_memory, int result_memory)
+        : ctx(c), args(a), index_bits_(index_bits), text_memory_(text_memory), result_memory_(result_memory),
+          timer(c.stream) {}
+
+    void run(SufrB200Result* out);
+
+   private:
+    Ctx& ctx;
+    const SufrB200Args& args;
+    uint32_t index_bits_;
+    int text_memory_, result_memory_;
+    EventTimer timer;
+    cudaStream_t st() const { return ctx.stream; }
+
+    uint64_t n = 0;       // text length
+    uint64_t s = 0;       // number of elements being sorted on this rank
+    KeySpec ks{};
+    SeedMaskInfo mask;
+    bool has_mask = false;
+    bool filter_active = false;
+    uint32_t alphabet = 0;
+    uint32_t refine_rounds = 0, doubling_rounds = 0;
+
+    DevBuf<uint8_t> d_text;     // transformed text
+    DevBuf<uint64_t> d_words;   // packed text
+    DevBuf<uint32_t> d_maskpos;
+    DevBuf<uint64_t> d_nstarts, d_nends;
+    std::vector<uint64_t> n_ranges_host;
+    DevBuf<uint32_t> d_sa, d_lcp;
+    DevBuf<uint32_t> d_counts;  // radix sort count matrix
+    uint64_t shard_offset = 0, total_suffixes = 0;
+    int t_keys_mark = -1;
+
+    template <typename T>
+    DevBuf<T> dalloc(size_t count) { return DevBuf<T>(ctx.pool, count ? count : 1); }
+    void launched(uint64_t k = 1) { ctx.launches += k; }
+
+    template <typename Op, typename In, typename Out>
+    typename Op::T scan_total(uint64_t count, In in, Op op, Out out) {
+        auto partials = dalloc<typename Op::T>(scan::partials_count(count));
+        scan::inclusive_scan(count, in, op, out, partials.get(), st());
+        launched(count ? 3 : 0);
+        typename Op::T total;
+        size_t idx = count ? (size_t)div_up(count, scan::CHUNK) : 0;
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&total, partials.get() + idx, sizeof(total), cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        return total;
+    }
+
+    void encode(const uint8_t* d_raw);
+    void find_n_runs();
+    void make_keys_and_sort(DevBuf<uint64_t>& keys_sorted);
+    void refine(DevBuf<uint64_t>& keys_sorted);
+    void doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
+                  uint64_t h);
+    void n_run_rule();
+    void apply_filter();
+    void segmented_sort_u64key(DevBuf<uint64_t>& ck, DevBuf<uint32_t>& pos, uint64_t m, int key_bits);
+};
+
+static int bits_for(uint64_t v) {  // number of bits needed to represent values 0..v
+    int b = 0;
+    while (v) { b++; v >>= 1; }
+    return b ? b : 1;
+}
+
+void Build::encode(const uint8_t* d_raw) {
+    d_text = dalloc<uint8_t>(n + 16);
+    auto d_present = dalloc<uint32_t>(256);
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_present.get(), 0, 256 * sizeof(uint32_t), st()));
+    if (n) {
+        transform_kernel<<<grid_for(n, 16), kBlock, 0, st()>>>(d_raw, d_text.get(), n, args.ignore_softmask,
+                                                               d_present.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+    }
+    uint32_t present[256];
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(present, d_present.get(), sizeof(present), cudaMemcpyDeviceToHost, st()));
+    SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+    uint8_t lut[256];
+    alphabet = 0;
+    for (int b = 0; b < 256; b++) lut[b] = present[b] ? (uint8_t)(++alphabet) : 0;
+    uint32_t bits = (uint32_t)bits_for(alphabet);
+    PackedText& pt = ks.pt;
+    pt.n = n;
+    pt.bits = bits;
+    pt.K = 64 / bits;
+    uint32_t used = pt.K * bits;
+    pt.keep_mask = used == 64 ? ~0ull : ~((1ull << (64 - used)) - 1ull);
+    pt.sym_mask = (1u << bits) - 1u;
+    uint64_t num_words = div_up(n, pt.K);
+    d_words = dalloc<uint64_t>(num_words + 2);
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_words.get() + num_words, 0, 2 * sizeof(uint64_t), st()));
+    auto d_lut = dalloc<uint8_t>(256);
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(d_lut.get(), lut, 256, cudaMemcpyHostToDevice, st()));
+    if (num_words) {
+        pack_kernel<<<grid_for(num_words), kBlock, 0, st()>>>(d_text.get(), n, d_lut.get(), bits, pt.K, num_words,
+                                                             d_words.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+    }
+    pt.words = d_words.get();
+    SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));  // lut / present are freed on return
+}
+
+void Build::find_n_runs() {
+    // sufr_builder.rs:174-195: maximal runs of 'N' of length >= 1000 that are terminated by another byte
+    ks.n_starts = nullptr;
+    ks.n_ends = nullptr;
+    ks.num_n_ranges = 0;
+    if (!args.allow_ambiguity || n == 0) return;
+    const uint8_t* t = d_text.get();
+    uint32_t nstart = scan_total(n, NRunStartIn{t}, scan::SumU32{}, CountOnly{});
+    if (nstart == 0) return;
+    auto starts = dalloc<uint64_t>(nstart);
+    auto ends = dalloc<uint64_t>(nstart);
+    scan_total(n, NRunStartIn{t}, scan::SumU32{}, IndexOut{starts.get()});
+    uint32_t nend = scan_total(n, NRunEndIn{t}, scan::SumU32{}, IndexOut{ends.get()});
+    // the k-th start pairs with the k-th end; a run that reaches the end of the text has no end
+    uint32_t npairs = nend < nstart ? nend : nstart;
+    if (npairs == 0) return;
+    NRunLongIn lin{starts.get(), ends.get(), 1000};
+    uint32_t nlong = scan_total(npairs, lin, scan::SumU32{}, CountOnly{});
+    if (nlong == 0) return;
+    d_nstarts = dalloc<uint64_t>(nlong);
+    d_nends = dalloc<uint64_t>(nlong);
+    scan_total(npairs, lin, scan::SumU32{}, NRunLongOut{starts.get(), ends.get(), d_nstarts.get(), d_nends.get()});
+    n_ranges_host.resize(2 * (size_t)nlong);
+    std::vector<uint64_t> hs(nlong), he(nlong);
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(hs.data(), d_nstarts.get(), nlong * 8, cudaMemcpyDeviceToHost, st()));
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(he.data(), d_nends.get(), nlong * 8, cudaMemcpyDeviceToHost, st()));
+    SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+    for (uint32_t i = 0; i < nlong; i++) {
+        n_ranges_host[2 * i] = hs[i];
+        n_ranges_host[2 * i + 1] = he[i];
+    }
+    if (!has_mask) {  // find_lcp consults the runs only in the MaxQueryLen branch (sufr_builder.rs:301-307)
+        ks.n_starts = d_nstarts.get();
+        ks.n_ends = d_nends.get();
+        ks.num_n_ranges = nlong;
+    }
+}
+
+void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted) {
+    const int descending = ks.mode != kModeFull;
+    const int world = args.world_size > 1 ? args.world_size : 1;
+    uint64_t lo = 0, hi = 0;
+    shard_offset = 0;
+    if (world > 1) {
+        // Splitters from a histogram of the top 12 key bits: every rank computes the same histogram of the
+        // replicated text, so ranks agree on the key ranges without communicating.
+        const uint32_t hbits = 12, bins = 1u << hbits;
+        auto d_hist = dalloc<unsigned long long>(bins);
+        SUFR_CUDA_CHECK(cudaMemsetAsync(d_hist.get(), 0, bins * 8, st()));
+        if (n) {
+            key_hist_kernel<<<grid_for(n, 8), kBlock, bins * sizeof(uint32_t), st()>>>(
+                ks, n, hbits, d_text.get(), filter_active ? 1 : 0, d_hist.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+        }
+        std::vector<unsigned long long> hist(bins);
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(hist.data(), d_hist.get(), bins * 8, cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        // bin boundaries b_0 = 0 <= b_1 <= ... <= b_world = bins with balanced counts
+        // (counts are of INDEXED suffixes, so shard offsets refer to the final suffix array)
+        std::vector<uint32_t> cut(world + 1, bins);
+        cut[0] = 0;
+        unsigned long long total = 0, acc = 0;
+        for (uint32_t b = 0; b < bins; b++) total += hist[b];
+        int g = 1;
+        for (uint32_t b = 0; b < bins && g < world; b++) {
+            acc += hist[b];
+            while (g < world && acc * world >= total * g) cut[g++] = b + 1;
+        }
+        uint32_t b0 = cut[args.rank], b1 = cut[args.rank + 1];
+        total_suffixes = total;
+        for (uint32_t b = 0; b < b0; b++) shard_offset += hist[b];
+        lo = (uint64_t)b0 << (64 - hbits);
+        hi = b1 >= bins ? 0 : (uint64_t)b1 << (64 - hbits);
+        if (b0 >= b1) { lo = ~0ull; hi = ~0ull; }  // empty shard: [max, max) selects nothing
+    }
+
+    DevBuf<uint64_t> keys_a, keys_b;
+    DevBuf<uint32_t> pos_a, pos_b;
+    if (world > 1) {
+        ShardIn in{ks, n, descending, lo, hi};
+        s = scan_total(n, in, scan::SumU32{}, CountOnly{});
+        keys_a = dalloc<uint64_t>(s);
+        pos_a = dalloc<uint32_t>(s);
+        if (s) scan_total(n, in, scan::SumU32{}, ShardOut{ks, n, descending, keys_a.get(), pos_a.get()});
+    } else {
+        s = n;
+        keys_a = dalloc<uint64_t>(s);
+        pos_a = dalloc<uint32_t>(s);
+        if (s) {
+            keygen_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(ks, n, descending, keys_a.get(), pos_a.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+        }
+    }
+    t_keys_mark = timer.mark();
+    keys_b = dalloc<uint64_t>(s);
+    pos_b = dalloc<uint32_t>(s);
+    d_counts = dalloc<uint32_t>(rsort::counts_words());
+    const int used = (int)(ks.pt.K * ks.pt.bits);
+    bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), s, 64 - used,
+                                                      64, d_counts.get(), st(), &ctx.launches);
+    if (in_b) {
+        keys_sorted = std::move(keys_b);
+        d_sa = std::move(pos_b);
+    } else {
+        keys_sorted = std::move(keys_a);
+        d_sa = std::move(pos_a);
+    }
+    // the ping-pong partners are released here (end of scope)
+}
+
+// Stable sort of (ck, pos) on the low `key_bits` bits of the composite key.
+void Build::segmented_sort_u64key(DevBuf<uint64_t>& ck, DevBuf<uint32_t>& pos, uint64_t m, int key_bits) {
+    auto ck_b = dalloc<uint64_t>(m);
+    auto pos_b = dalloc<uint32_t>(m);
+    bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(ck.get(), ck_b.get(), pos.get(), pos_b.get(), m, 0, key_bits,
+                                                      d_counts.get(), st(), &ctx.launches);
+    if (in_b) {
+        ck = std::move(ck_b);
+        pos = std::move(pos_b);
+    }
+}
+
+void Build::refine(DevBuf<uint64_t>& keys_sorted) {
+    const uint32_t K = ks.pt.K;
+    const int used = (int)(K * ks.pt.bits);
+    d_lcp = dalloc<uint32_t>(s);
+    if (s == 0) return;
+
+    // round 0: boundaries of the initial sort
+    uint32_t word = 0;
+    int final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
+    ViewAll v0{keys_sorted.get(), d_sa.get()};
+    resolve_kernel<ViewAll><<<grid_for(s, 4), kBlock, 0, st()>>>(v0, s, ks, word, final_word, 1, d_lcp.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+    if (final_word) {
+        keys_sorted.reset();
+        return;
+    }
+    unsigned long long tot = scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{}, CountOnlyU64{});
+    uint64_t m = (uint32_t)tot, nseg = tot >> 32;
+    if (m == 0) {
+        keys_sorted.reset();
+        return;
+    }
+    auto slot = dalloc<uint32_t>(m);
+    auto pos = dalloc<uint32_t>(m);
+    auto seg = dalloc<uint32_t>(m);
+    scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{}, ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()});
+    keys_sorted.reset();
+
+    // Full sort: after kMaxWordRounds words switch to prefix doubling (depth doubles per round).
+    const uint32_t kMaxWordRounds = 3;
+    while (m > 0) {
+        if (ks.mode == kModeFull && word >= kMaxWordRounds) {
+            doubling(slot, pos, seg, m, nseg, (uint64_t)(word + 1) * K);
+            return;
+        }
+        word++;
+        refine_rounds++;
+        final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
+        auto keys = dalloc<uint64_t>(m);
+        auto segpos = dalloc<uint64_t>(m);
+        active_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, word, pos.get(), seg.get(), keys.get(),
+                                                               segpos.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        {   // stable sort by (segment, key word): LSD, key word first, then the segment bits
+            auto keys_b = dalloc<uint64_t>(m);
+            auto segpos_b = dalloc<uint64_t>(m);
+            bool in_b = rsort::sort_pairs<uint64_t, uint64_t>(keys.get(), keys_b.get(), segpos.get(), segpos_b.get(), m,
+                                                              64 - used, 64, d_counts.get(), st(), &ctx.launches);
+            if (in_b) { std::swap(keys, keys_b); std::swap(segpos, segpos_b); }
+            if (nseg > 1) {
+                int sb = bits_for(nseg - 1);
+                in_b = rsort::sort_pairs<uint64_t, uint64_t>(segpos.get(), segpos_b.get(), keys.get(), keys_b.get(), m, 32,
+                                                             32 + sb, d_counts.get(), st(), &ctx.launches);
+                if (in_b) { std::swap(keys, keys_b); std::swap(segpos, segpos_b); }
+            }
+        }
+        writeback_segpos_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, segpos.get(), slot.get(), pos.get(), d_sa.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        segpos.reset();
+        ViewActive va{keys.get(), pos.get(), seg.get(), slot.get()};
+        resolve_kernel<ViewActive><<<grid_for(m, 2), kBlock, 0, st()>>>(va, m, ks, word, final_word, 0, d_lcp.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        if (final_word) return;
+        tot = scan_total(m, ActiveIn<ViewActive>{va, m, 0}, scan::SumU64{}, CountOnlyU64{});
+        uint64_t m2 = (uint32_t)tot, nseg2 = tot >> 32;
+        if (m2 == 0) return;
+        auto slot2 = dalloc<uint32_t>(m2);
+        auto pos2 = dalloc<uint32_t>(m2);
+        auto seg2 = dalloc<uint32_t>(m2);
+        scan_total(m, ActiveIn<ViewActive>{va, m, 0}, scan::SumU64{},
+                   ActiveOut<ViewActive>{va, slot2.get(), pos2.get(), seg2.get()});
+        slot = std::move(slot2);
+        pos = std::move(pos2);
+        seg = std::move(seg2);
+        m = m2;
+        nseg = nseg2;
+    }
+}
+
+// Prefix doubling on the still-unresolved groups (Larsson-Sadakane style: only active groups are sorted).
+// Needs the rank of EVERY text position, hence only valid when all positions were sorted on this rank.
+void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
+                     uint64_t h) {
+    if (s != n)
+        throw Error(SUFR_B200_ERR_UNSUPPORTED,
+                    "text has repeats deeper than the word-refinement limit; prefix doubling needs an unsharded build");
+    auto isa = dalloc<uint32_t>(n);
+    isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+    scan_total(m, GroupStartIn{seg.get()}, scan::MaxU32{}, GroupRankOut{slot.get(), pos.get(), isa.get()});
+    while (m > 0) {
+        if (doubling_rounds > 64) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling did not converge");
+        doubling_rounds++;
+        auto ck = dalloc<uint64_t>(m);
+        doubling_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, n, h, pos.get(), seg.get(), isa.get(), ck.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        segmented_sort_u64key(ck, pos, m, 32 + (nseg > 1 ? bits_for(nseg - 1) : 0));
+        writeback_pos_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, pos.get(), slot.get(), d_sa.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        uint32_t mark = kLcpLowerBound | (uint32_t)(h < 0x7FFFFFFFull ? h : 0x7FFFFFFFull);
+        scan_total(m, DoublingStartIn{ck.get()}, scan::MaxU32{},
+                   DoublingRankOut{ck.get(), slot.get(), pos.get(), isa.get(), d_lcp.get(), mark});
+        unsigned long long tot = scan_total(m, DoublingActiveIn{ck.get(), m}, scan::SumU64{}, CountOnlyU64{});
+        uint64_t m2 = (uint32_t)tot, nseg2 = tot >> 32;
+        if (m2 == 0) break;
+        auto slot2 = dalloc<uint32_t>(m2);
+        auto pos2 = dalloc<uint32_t>(m2);
+        auto seg2 = dalloc<uint32_t>(m2);
+        scan_total(m, DoublingActiveIn{ck.get(), m}, scan::SumU64{},
+                   DoublingActiveOut{slot.get(), pos.get(), slot2.get(), pos2.get(), seg2.get()});
+        slot = std::move(slot2);
+        pos = std::move(pos2);
+        seg = std::move(seg2);
+        m = m2;
+        nseg = nseg2;
+        h *= 2;
+    }
+}
+
+void Build::n_run_rule() {
+    if (ks.num_n_ranges == 0 || s < 2) return;
+    n_rule_lcp_kernel<<<grid_for(s, 2), kBlock, 0, st()>>>(ks, d_text.get(), s, d_sa.get(), d_lcp.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+    NTieIn in{ks, d_text.get(), d_sa.get(), s};
+    unsigned long long tot = scan_total(s, in, scan::SumU64{}, CountOnlyU64{});
+    uint64_t m = (uint32_t)tot, nseg = tot >> 32;
+    if (m == 0) return;
+    auto slot = dalloc<uint32_t>(m);
+    auto pos = dalloc<uint32_t>(m);
+    auto ck = dalloc<uint64_t>(m);
+    scan_total(s, in, scan::SumU64{}, NTieOut{d_sa.get(), slot.get(), pos.get(), ck.get()});
+    segmented_sort_u64key(ck, pos, m, 32 + (nseg > 1 ? bits_for(nseg - 1) : 0));
+    writeback_pos_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, pos.get(), slot.get(), d_sa.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+}
+
+void Build::apply_filter() {
+    if (!filter_active || s == 0) return;
+    FilterCountIn cin{d_text.get(), d_sa.get()};
+    uint32_t kept = scan_total(s, cin, scan::SumU32{}, CountOnly{});
+    if (kept == s) return;
+    auto scanned = dalloc<uint32_t>(s);
+    scan_total(s, FilterLcpIn{d_text.get(), d_sa.get(), d_lcp.get()}, scan::SegMinU64{},
+               FilterLcpOut{d_text.get(), d_sa.get(), nullptr, scanned.get()});
+    auto sa2 = dalloc<uint32_t>(kept);
+    auto idx = dalloc<uint32_t>(kept);
+    scan_total(s, cin, scan::SumU32{}, FilterSaOut{d_sa.get(), sa2.get(), idx.get()});
+    auto lcp2 = dalloc<uint32_t>(kept);
+    if (kept) {
+        gather_u32_kernel<<<grid_for(kept, 2), kBlock, 0, st()>>>(kept, idx.get(), scanned.get(), lcp2.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+    }
+    d_sa = std::move(sa2);
+    d_lcp = std::move(lcp2);
+    s = kept;
+}
+
+void Build::run(SufrB200Result* out) {
+    n = args.text_len;
+    if (n >= 0xFFFFFFFFull)
+        throw Error(SUFR_B200_ERR_UNSUPPORTED,
+                    "text_len >= 2^32 - 1 needs 64-bit positions inside the sort; this build supports u64 OUTPUT for "
+                    "texts below that length only");
+    if (index_bits_ == 0) index_bits_ = 32;  // suffix_array.rs:461 (text_len < u32::MAX here)
+    if (index_bits_ != 32 && index_bits_ != 64) throw Error(SUFR_B200_ERR_ARGUMENT, "index_bits must be 0, 32 or 64");
+    if (args.world_size > 1 && (args.rank < 0 || args.rank >= args.world_size))
+        throw Error(SUFR_B200_ERR_ARGUMENT, "rank out of range");
+
+    // sufr_builder.rs:163-172
+    if (args.seed_mask && args.has_max_query_len)
+        throw Error(SUFR_B200_ERR_ARGUMENT, "Cannot use max_query_len and seed_mask together");
+    if (args.seed_mask) {
+        if (!parse_seed_mask(args.seed_mask, mask))
+            throw Error(SUFR_B200_ERR_ARGUMENT, std::string("Invalid seed mask '") + args.seed_mask + "'");
+        has_mask = true;
+    }
+    ks.mode = has_mask ? kModeMask : (args.has_max_query_len && args.max_query_len > 0 ? kModeMaxQueryLen : kModeFull);
+    ks.cap = has_mask ? mask.weight : (ks.mode == kModeMaxQueryLen ? args.max_query_len : ~0ull);
+    ks.weight = has_mask ? (uint32_t)mask.weight : 0;
+    ks.mask_len = has_mask ? (uint32_t)mask.bytes.size() : 0;
+    ks.mask_pos = nullptr;
+    filter_active = args.is_dna && !args.allow_ambiguity;  // sufr_builder.rs:446-449
+
+    SUFR_CUDA_CHECK(cudaSetDevice(ctx.device));
+    ctx.pool.reset_peak();
+    const uint64_t launches0 = ctx.launches;
+    // working set: text n, packed <= n, keys 2x8n, positions 2x4n, lcp 4n (+ output widening 16n for u64)
+    {
+        uint64_t per = 30 + (index_bits_ == 64 ? 16 : 0);
+        uint64_t shard_n = args.world_size > 1 ? n / args.world_size + n / 8 : n;
+        ctx.pool.reserve((size_t)(2 * n + per * shard_n + (64ull << 20)));
+    }
+
+    SufrB200Timings tm{};
+    // ---- text on the device
+    DevBuf<uint8_t> d_raw_owned;
+    const uint8_t* d_raw = args.text;
+    if (text_memory_ == SUFR_B200_MEM_HOST) {
+        d_raw_owned = dalloc<uint8_t>(n + 16);
+        int e0 = timer.mark();
+        if (n) SUFR_CUDA_CHECK(cudaMemcpyAsync(d_raw_owned.get(), args.text, n, cudaMemcpyHostToDevice, st()));
+        int e1 = timer.mark();
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        tm.h2d_ms = timer.ms(e0, e1);
+        d_raw = d_raw_owned.get();
+    }
+
+    int t0 = timer.mark();
+    encode(d_raw);
+    d_raw_owned.reset();
+    if (has_mask) {
+        std::vector<uint32_t> mp(mask.positions.begin(), mask.positions.end());
+        d_maskpos = dalloc<uint32_t>(mp.size());
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(d_maskpos.get(), mp.data(), mp.size() * 4, cudaMemcpyHostToDevice, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        ks.mask_pos = d_maskpos.get();
+    }
+    find_n_runs();
+    int t1 = timer.mark();
+
+    DevBuf<uint64_t> keys_sorted;
+    make_keys_and_sort(keys_sorted);
+    int t2 = timer.mark();
+    refine(keys_sorted);
+    keys_sorted.reset();
+    int t3 = timer.mark();
+
+    // finish: filter first (so that deep LCPs between non-indexed suffixes are never computed), then the
+    // remaining lower-bound LCP marks, then the N-run rule.
+    apply_filter();
+    int t4 = timer.mark();
+    if (doubling_rounds && s) {
+        lcp_complete_kernel<<<grid_for(s, 1), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+    }
+    int t5 = timer.mark();
+    n_run_rule();
+
+    // shard bookkeeping
+    if (args.world_size <= 1) total_suffixes = s;
+    uint64_t first = 0, last = 0;
+    if (s) {
+        uint32_t fl[2];
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&fl[0], d_sa.get(), 4, cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&fl[1], d_sa.get() + (s - 1), 4, cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        first = fl[0];
+        last = fl[1];
+    }
+
+    // outputs
+    auto owner = std::make_unique<ResultOwner>();
+    owner->ctx = &ctx;
+    owner->memory = result_memory_;
+    const size_t w = index_bits_ / 8;
+    DevBuf<unsigned long long> sa64, lcp64;
+    void* d_sa_out = d_sa.get();
+    void* d_lcp_out = d_lcp.get();
+    if (index_bits_ == 64) {
+        sa64 = dalloc<unsigned long long>(s);
+        lcp64 = dalloc<unsigned long long>(s);
+        if (s) {
+            widen_kernel<<<grid_for(s, 2), kBlock, 0, st()>>>(s, d_sa.get(), sa64.get());
+            widen_kernel<<<grid_for(s, 2), kBlock, 0, st()>>>(s, d_lcp.get(), lcp64.get());
+            SUFR_KERNEL_CHECK();
+            launched(2);
+        }
+        d_sa.reset();
+        d_lcp.reset();
+        d_sa_out = sa64.get();
+        d_lcp_out = lcp64.get();
+    }
+    int t6 = timer.mark();
+    SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+    tm.encode_ms = timer.ms(t0, t1);
+    tm.keys_ms = timer.ms(t1, t_keys_mark);
+    tm.sort_ms = timer.ms(t_keys_mark, t2);
+    tm.refine_ms = timer.ms(t2, t3);
+    tm.finish_ms = timer.ms(t3, t4) + timer.ms(t5, t6);
+    tm.lcp_ms = timer.ms(t4, t5);
+    tm.total_ms = timer.ms(t0, t6);
+
+    if (result_memory_ == SUFR_B200_MEM_DEVICE) {
+        owner->text = d_text.release();
+        if (index_bits_ == 64) {
+            owner->sa = sa64.release();
+            owner->lcp = lcp64.release();
+        } else {
+            owner->sa = d_sa.release();
+            owner->lcp = d_lcp.release();
+        }
+    } else {
+        int e0 = timer.mark();
+        SUFR_CUDA_CHECK(cudaMallocHost(&owner->text, n ? n : 1));
+        SUFR_CUDA_CHECK(cudaMallocHost(&owner->sa, s ? s * w : 1));
+        SUFR_CUDA_CHECK(cudaMallocHost(&owner->lcp, s ? s * w : 1));
+        int e1 = timer.mark();
+        if (n) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
+        if (s) {
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa_out, s * w, cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->lcp, d_lcp_out, s * w, cudaMemcpyDeviceToHost, st()));
+        }
+        int e2 = timer.mark();
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        (void)e0;
+        tm.d2h_ms = timer.ms(e1, e2);
+    }
+    if (!n_ranges_host.empty()) {
+        owner->n_ranges = (uint64_t*)malloc(n_ranges_host.size() * 8);
+        memcpy(owner->n_ranges, n_ranges_host.data(), n_ranges_host.size() * 8);
+    }
+
+    memset(out, 0, sizeof(*out));
+    out->index_bits = index_bits_;
+    out->memory = (uint32_t)result_memory_;
+    out->text_len = n;
+    out->num_suffixes = s;
+    out->total_suffixes = total_suffixes;
+    out->shard_offset = shard_offset;
+    out->first_suffix = first;
+    out->last_suffix = last;
+    out->text = (uint8_t*)owner->text;
+    out->sa = owner->sa;
+    out->lcp = owner->lcp;
+    out->n_ranges = owner->n_ranges;
+    out->num_n_ranges = n_ranges_host.size() / 2;
+    out->timings = tm;
+    out->kernel_launches = ctx.launches - launches0;
+    out->peak_device_bytes = ctx.pool.peak();
+    out->alphabet_size = alphabet;
+    out->bits_per_symbol = ks.pt.bits;
+    out->refine_rounds = refine_rounds;
+    out->doubling_rounds = doubling_rounds;
+    out->owner = owner.release();
+}
+
+static void free_owner(ResultOwner* o) {
+    if (!o) return;
+    if (o->memory == SUFR_B200_MEM_DEVICE) {
+        if (o->ctx) {
+            std::lock_guard<std::mutex> lock(o->ctx->mu);
+            if (o->text) o->ctx->pool.free(o->text);
+            if (o->sa) o->ctx->pool.free(o->sa);
+            if (o->lcp) o->ctx->pool.free(o->lcp);
+        }
+    } else {
+        if (o->text) cudaFreeHost(o->text);
+        if (o->sa) cudaFreeHost(o->sa);
+        if (o->lcp) cudaFreeHost(o->lcp);
+    }
+    free(o->n_ranges);
+    if (o->owns_ctx && o->ctx) {
+        cudaStreamDestroy(o->ctx->stream);
+        delete o->ctx;
+    }
+    delete o;
+}
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return SUFR_B200_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "host allocation failed";
+        return SUFR_B200_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return SUFR_B200_ERR_INTERNAL;
+    }
+}
+
+static Ctx* make_ctx(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw Error(SUFR_B200_ERR_CUDA, "no CUDA device available: the sufr_b200 build path has no CPU fallback");
+    }
+    if (device < 0 || device >= count) throw Error(SUFR_B200_ERR_ARGUMENT, "invalid CUDA device ordinal");
+    SUFR_CUDA_CHECK(cudaSetDevice(device));
+    auto c = std::make_unique<Ctx>();
+    c->device = device;
+    SUFR_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    return c.release();
+}
+
+// Rebuilds the KeySpec of a finished result far enough to compute one pair LCP (seam repair).
+}  // namespace sufr
+
+using namespace sufr;
+
+extern "C" {
+
+int sufr_b200_abi_version(void) { return SUFR_B200_ABI_VERSION; }
+
+const char* sufr_b200_last_error(void) { return g_last_error.c_str(); }
+
+int sufr_b200_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+int sufr_b200_ctx_create(int device, SufrB200Ctx** out) {
+    return guarded([&] {
+        if (!out) throw Error(SUFR_B200_ERR_ARGUMENT, "out is NULL");
+        *out = reinterpret_cast<SufrB200Ctx*>(make_ctx(device));
+    });
+}
+
+void sufr_b200_ctx_destroy(SufrB200Ctx* c) {
+    if (!c) return;
+    Ctx* ctx = reinterpret_cast<Ctx*>(c);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->pool.release_all();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sufr_b200_ctx_reserve(SufrB200Ctx* c, uint64_t text_len, uint32_t index_bits) {
+    return guarded([&] {
+        Ctx* ctx = reinterpret_cast<Ctx*>(c);
+        if (!ctx) throw Error(SUFR_B200_ERR_ARGUMENT, "ctx is NULL");
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx->device));
+        uint64_t per = 32 + (index_bits == 64 ? 16 : 0);
+        ctx->pool.reserve((size_t)(per * text_len + (64ull << 20)));
+    });
+}
+
+void sufr_b200_ctx_trim(SufrB200Ctx* c) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(c);
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaSetDevice(ctx->device);
+    ctx->pool.trim();
+}
+
+int sufr_b200_build(SufrB200Ctx* c, const SufrB200Args* args, uint32_t index_bits, int text_memory, int result_memory,
+                    SufrB200Result* out) {
+    return guarded([&] {
+        Ctx* ctx = reinterpret_cast<Ctx*>(c);
+        if (!ctx || !args || !out) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (args->text_len && !args->text) throw Error(SUFR_B200_ERR_ARGUMENT, "text is NULL");
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        try {
+            Build b(*ctx, *args, index_bits, text_memory, result_memory);
+            b.run(out);
+        } catch (...) {
+            cudaStreamSynchronize(ctx->stream);
+            throw;
+        }
+    });
+}
+
+void sufr_b200_result_free(SufrB200Ctx*, SufrB200Result* r) {
+    if (!r) return;
+    free_owner(static_cast<ResultOwner*>(r->owner));
+    memset(r, 0, sizeof(*r));
+}
+
+int sufr_b200_patch_seam(SufrB200Ctx* c, const SufrB200Args* args, SufrB200Result* r, uint64_t prev_last_suffix) {
+    return guarded([&] {
+        Ctx* ctx = reinterpret_cast<Ctx*>(c);
+        if (!ctx || !args || !r) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (r->num_suffixes == 0) return;
+        // The seam needs the text only: recompute the pair LCP on the host from the transformed text
+        // when the result is on the host, on the device otherwise.
+        SeedMaskInfo mask;
+        bool has_mask = args->seed_mask && parse_seed_mask(args->seed_mask, mask);
+        uint64_t q = (!has_mask && args->has_max_query_len) ? args->max_query_len : 0;
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx->device));
+        const uint64_t a = prev_last_suffix, b = r->first_suffix, n = r->text_len;
+        if (a >= n || b >= n) throw Error(SUFR_B200_ERR_ARGUMENT, "suffix out of range");
+        uint64_t l = 0;
+        if (r->memory == SUFR_B200_MEM_HOST) {
+            l = host_pair_lcp(r->text, n, a, b, has_mask ? &mask : nullptr, q, r->n_ranges, r->num_n_ranges);
+        } else {
+            // Device result: compare growing windows of the two suffixes on the host (the two suffixes come
+            // from different key ranges, so they almost always differ within the first few bytes).
+            uint64_t win = has_mask ? mask.bytes.size() + 64 : 4096;
+            while (true) {
+                uint64_t la = std::min(win, n - a), lb = std::min(win, n - b);
+                std::vector<uint8_t> buf(la + lb);
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(buf.data(), r->text + a, la, cudaMemcpyDeviceToHost, ctx->stream));
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(buf.data() + la, r->text + b, lb, cudaMemcpyDeviceToHost, ctx->stream));
+                SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                // rebase: the window of suffix a is buf[0, la), of suffix b is buf[la, la + lb)
+                uint64_t ea = 0, eb = 0;
+                bool both_n = false;
+                if (!has_mask && r->num_n_ranges) {
+                    // N-run shortcut needs only the recorded ranges
+                    uint64_t lo = 0, hi = r->num_n_ranges;
+                    auto find = [&](uint64_t p, uint64_t& end) {
+                        lo = 0; hi = r->num_n_ranges;
+                        while (lo < hi) {
+                            uint64_t mid = (lo + hi) / 2;
+                            if (r->n_ranges[2 * mid] <= p && p < r->n_ranges[2 * mid + 1]) { end = r->n_ranges[2 * mid + 1]; return true; }
+                            if (r->n_ranges[2 * mid] < p) lo = mid + 1; else hi = mid;
+                        }
+                        return false;
+                    };
+                    both_n = find(a, ea) && find(b, eb);
+                }
+                if (both_n) { l = std::min(ea - a, eb - b); break; }
+                if (has_mask) {
+                    l = 0;
+                    for (uint64_t k = 0; k < mask.positions.size(); k++) {
+                        uint64_t o = mask.positions[k];
+                        if (a + o >= n || b + o >= n || buf[o] != buf[la + o]) break;
+                        l++;
+                    }
+                    break;
+                }
+                uint64_t lim = std::min(la, lb);
+                if (q && q < lim) lim = q;
+                l = 0;
+                while (l < lim && buf[l] == buf[la + l]) l++;
+                bool hit_window = (l == lim) && !(q && lim == q) && lim < std::min(n - a, n - b);
+                if (!hit_window) break;
+                win *= 16;
+            }
+        }
+        if (r->memory == SUFR_B200_MEM_DEVICE) {
+            if (r->index_bits == 32) {
+                uint32_t v = (uint32_t)l;
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(r->lcp, &v, 4, cudaMemcpyHostToDevice, ctx->stream));
+            } else {
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(r->lcp, &l, 8, cudaMemcpyHostToDevice, ctx->stream));
+            }
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        } else {
+            if (r->index_bits == 32) ((uint32_t*)r->lcp)[0] = (uint32_t)l;
+            else ((uint64_t*)r->lcp)[0] = l;
+        }
+    });
+}
+
+int sufr_b200_write(const SufrB200Args* args, const SufrB200Result* r) {
+    return guarded([&] {
+        if (!args || !r) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (r->memory != SUFR_B200_MEM_HOST) throw Error(SUFR_B200_ERR_ARGUMENT, "sufr_b200_write needs a host result");
+        write_sufr_file(*args, *r);
+    });
+}
+
+int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out) {
+    SufrB200Result local;
+    SufrB200Result* res = out ? out : &local;
+    int rc = guarded([&] {
+        if (!args) throw Error(SUFR_B200_ERR_ARGUMENT, "args is NULL");
+        std::unique_ptr<Ctx> ctx(make_ctx(device));
+        try {
+            {
+                std::lock_guard<std::mutex> lock(ctx->mu);
+                Build b(*ctx, *args, 0, SUFR_B200_MEM_HOST, SUFR_B200_MEM_HOST);
+                b.run(res);
+            }
+            write_sufr_file(*args, *res);
+        } catch (...) {
+            cudaStreamSynchronize(ctx->stream);
+            ctx->pool.release_all();
+            cudaStreamDestroy(ctx->stream);
+            throw;
+        }
+        // host result does not need the context any more
+        static_cast<ResultOwner*>(res->owner)->ctx = nullptr;
+        ctx->pool.release_all();
+        cudaStreamDestroy(ctx->stream);
+    });
+    if (rc == SUFR_B200_OK && !out) sufr_b200_result_free(nullptr, &local);
+    return rc;
+}
+
+int64_t sufr_b200_seed_mask(const char* mask, uint8_t* bytes, uint64_t* positions, uint64_t* differences) {
+    SeedMaskInfo m;
+    if (!mask || !parse_seed_mask(mask, m)) return -1;
+    for (size_t i = 0; i < m.bytes.size(); i++)
+        if (bytes) bytes[i] = m.bytes[i];
+    for (size_t i = 0; i < m.positions.size(); i++) {
+        if (positions) positions[i] = m.positions[i];
+        if (differences) differences[i] = m.positions[i] - i;
+    }
+    return (int64_t)m.weight;
+}
+
+uint64_t sufr_b200_find_lcp_full_offset(uint64_t lcp, const char* mask) {
+    if (!mask) return lcp;
+    SeedMaskInfo m;
+    if (!parse_seed_mask(mask, m)) return (uint64_t)-1;
+    return lcp_full_offset(lcp, m);
+}
+
+int sufr_b200_read_sequence_file(const char* path, uint8_t delim, SufrB200Sequences* out) {
+    return guarded([&] {
+        if (!path || !out) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        read_sequence_file(path, delim, out);
+    });
+}
+
+void sufr_b200_sequences_free(SufrB200Sequences* s) { free_sequences(s); }
+
+int sufr_b200_synth_dna(SufrB200Ctx* c, uint8_t* device_text, uint64_t text_len, uint64_t seed,
+                        const uint64_t* record_starts, uint64_t num_records, uint8_t delimiter) {
+    return guarded([&] {
+        Ctx* ctx = reinterpret_cast<Ctx*>(c);
+        if (!ctx || !device_text) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx->device));
+        if (text_len == 0) return;
+        synth_dna_kernel<<<grid_for(text_len, 4), kBlock, 0, ctx->stream>>>(device_text, text_len, seed);
+        SUFR_KERNEL_CHECK();
+        DevBuf<uint64_t> d_starts(ctx->pool, num_records ? num_records : 1);
+        if (num_records)
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(d_starts.get(), record_starts, num_records * 8, cudaMemcpyHostToDevice,
+                                            ctx->stream));
+        uint64_t threads = num_records ? num_records : 1;
+        synth_marks_kernel<<<(unsigned)div_up(threads, 256), 256, 0, ctx->stream>>>(device_text, text_len, d_starts.get(),
+                                                                                   num_records, delimiter);
+        SUFR_KERNEL_CHECK();
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// Shared declarations for the sufr_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace sufr {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define SUFR_CUDA_CHECK(expr)                                                                        \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            throw ::sufr::Error(100 + (int)_e, std::string("CUDA error ") + cudaGetErrorName(_e) +   \
+                                                   " (" + cudaGetErrorString(_e) + ") at " +         \
+                                                   __FILE__ + ":" + std::to_string(__LINE__) + ": " + #expr); \
+    } while (0)
+
+#define SUFR_KERNEL_CHECK() SUFR_CUDA_CHECK(cudaGetLastError())
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline uint32_t div_up_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// LCP array encoding while under construction (u32):
+//   kLcpPending        : element is not a group head yet (shares all words so far with its predecessor)
+//   kLcpLowerBound | h : boundary created by a prefix-doubling round; true LCP is in [h, 2h)
+constexpr uint32_t kLcpPending = 0xFFFFFFFFu;
+constexpr uint32_t kLcpLowerBound = 0x80000000u;
+
+}  // namespace sufr

@@ -1,0 +1,254 @@
+#include "host_io.hpp"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace sufr {
+
+// ------------------------------------------------------------------ SeedMask (types.rs:80-200)
+bool parse_seed_mask(const char* mask, SeedMaskInfo& out) {
+    // valid iff it matches ^1+0[01]*1$ (types.rs:163-166): only 0/1, starts and ends with 1, has a 0
+    size_t len = strlen(mask);
+    if (len < 3 || mask[0] != '1' || mask[len - 1] != '1') return false;
+    bool zero = false;
+    for (size_t i = 0; i < len; i++) {
+        if (mask[i] == '0') zero = true;
+        else if (mask[i] != '1') return false;
+    }
+    if (!zero) return false;
+    out.mask = mask;
+    out.bytes.clear();
+    out.positions.clear();
+    for (size_t i = 0; i < len; i++) {
+        out.bytes.push_back(mask[i] == '1' ? 1 : 0);
+        if (mask[i] == '1') out.positions.push_back(i);
+    }
+    out.weight = out.positions.size();
+    return true;
+}
+
+uint64_t lcp_full_offset(uint64_t lcp, const SeedMaskInfo& m) {
+    if (lcp == 0 || lcp > m.bytes.size()) return lcp;
+    uint64_t offset = m.positions[lcp - 1];
+    uint64_t next_offset = lcp < m.positions.size() ? m.positions[lcp] : 0;
+    if (next_offset > offset && next_offset - offset > 1) return next_offset;
+    return offset + 1;
+}
+
+static bool in_n_run(const uint64_t* r, uint64_t k, uint64_t p, uint64_t& end) {
+    uint64_t lo = 0, hi = k;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) / 2;
+        if (r[2 * mid] <= p && p < r[2 * mid + 1]) { end = r[2 * mid + 1]; return true; }
+        if (r[2 * mid] < p) lo = mid + 1; else hi = mid;
+    }
+    return false;
+}
+
+uint64_t host_pair_lcp(const uint8_t* text, uint64_t n, uint64_t a, uint64_t b, const SeedMaskInfo* mask, uint64_t q,
+                       const uint64_t* n_ranges, uint64_t num_n_ranges) {
+    if (mask) {
+        uint64_t c = 0;
+        for (uint64_t k = 0; k < mask->positions.size(); k++) {
+            uint64_t x = a + mask->positions[k], y = b + mask->positions[k];
+            if (x >= n || y >= n || text[x] != text[y]) break;
+            c++;
+        }
+        return c;
+    }
+    uint64_t ea, eb;
+    if (num_n_ranges && in_n_run(n_ranges, num_n_ranges, a, ea) && in_n_run(n_ranges, num_n_ranges, b, eb))
+        return std::min(ea - a, eb - b);
+    uint64_t lim = std::min(n - a, n - b);
+    if (q && q < lim) lim = q;
+    uint64_t c = 0;
+    while (c < lim && text[a + c] == text[b + c]) c++;
+    return c;
+}
+
+// ------------------------------------------------------------------ `.sufr` writer
+static void put_u64(std::vector<uint8_t>& out, uint64_t v) {  // util.rs:138-151
+    for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i)));
+}
+
+static void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const std::string& path) {
+    const char* p = (const char*)buf;
+    while (len) {
+        size_t chunk = len > (1u << 30) ? (1u << 30) : len;
+        ssize_t w = pwrite(fd, p, chunk, (off_t)off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
+        }
+        p += w;
+        off += (uint64_t)w;
+        len -= (size_t)w;
+    }
+}
+
+void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
+    const std::string path = args.path ? args.path : "out.sufr";  // sufr_builder.rs:215
+    const size_t w = r.index_bits / 8;
+    SeedMaskInfo mask;
+    const bool has_mask = args.seed_mask && parse_seed_mask(args.seed_mask, mask);
+
+    // header (sufr_builder.rs:826-867); all integers little-endian
+    std::vector<uint8_t> head;
+    head.push_back(6);  // OUTFILE_VERSION, types.rs:16
+    head.push_back(args.is_dna ? 1 : 0);
+    head.push_back(args.allow_ambiguity ? 1 : 0);
+    head.push_back(args.ignore_softmask ? 1 : 0);
+    put_u64(head, r.text_len);
+    const size_t locs_pos = head.size();
+    put_u64(head, 0);
+    put_u64(head, 0);
+    put_u64(head, 0);
+    put_u64(head, r.total_suffixes);
+    put_u64(head, has_mask ? 0 : (args.has_max_query_len ? args.max_query_len : 0));
+    put_u64(head, args.num_sequences);
+    for (uint64_t i = 0; i < args.num_sequences; i++) {
+        uint64_t v = args.sequence_starts[i];
+        for (size_t k = 0; k < w; k++) head.push_back((uint8_t)(v >> (8 * k)));
+    }
+    if (has_mask) {
+        put_u64(head, mask.bytes.size());
+        head.insert(head.end(), mask.bytes.begin(), mask.bytes.end());
+    } else {
+        put_u64(head, 0);
+    }
+    const uint64_t text_pos = head.size();
+    const uint64_t sa_pos = text_pos + r.text_len;
+    const uint64_t lcp_pos = sa_pos + r.total_suffixes * w;
+    const uint64_t names_pos = lcp_pos + r.total_suffixes * w;
+    {
+        std::vector<uint8_t> locs;
+        put_u64(locs, text_pos);
+        put_u64(locs, sa_pos);
+        put_u64(locs, lcp_pos);
+        memcpy(head.data() + locs_pos, locs.data(), locs.size());
+    }
+    // bincode 1.3 Vec<String>: u64 count, then per string u64 length + bytes (sufr_builder.rs:909)
+    std::vector<uint8_t> tail;
+    put_u64(tail, args.num_sequences);
+    for (uint64_t i = 0; i < args.num_sequences; i++) {
+        const char* nm = args.sequence_names ? args.sequence_names[i] : "";
+        size_t len = strlen(nm);
+        put_u64(tail, len);
+        tail.insert(tail.end(), nm, nm + len);
+    }
+
+    const bool sharded = args.world_size > 1;
+    const bool leader = !sharded || args.rank == 0;
+    int fd = open(path.c_str(), O_WRONLY | O_CREAT | (sharded ? 0 : O_TRUNC), 0644);
+    if (fd < 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));  // sufr_builder.rs:820
+    try {
+        if (leader) {
+            pwrite_all(fd, head.data(), head.size(), 0, path);
+            pwrite_all(fd, r.text, r.text_len, text_pos, path);
+            pwrite_all(fd, tail.data(), tail.size(), names_pos, path);
+            if (sharded && ftruncate(fd, (off_t)(names_pos + tail.size())) != 0)
+                throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
+        }
+        pwrite_all(fd, r.sa, r.num_suffixes * w, sa_pos + r.shard_offset * w, path);
+        pwrite_all(fd, r.lcp, r.num_suffixes * w, lcp_pos + r.shard_offset * w, path);
+    } catch (...) {
+        close(fd);
+        throw;
+    }
+    if (close(fd) != 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
+}
+
+// ------------------------------------------------------------------ FASTA / FASTQ ingest (util.rs:51-89)
+// The reference delegates parsing to needletail 0.6 (not vendored).  This follows its documented
+// behaviour for plain-text input: FASTA records may span lines, FASTQ records are 4 lines, '\r' is
+// stripped, the id is the header up to the first whitespace.
+void read_sequence_file(const char* path, uint8_t delim, SufrB200Sequences* out) {
+    memset(out, 0, sizeof(*out));
+    FILE* f = fopen(path, "rb");
+    if (!f) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": " + strerror(errno));
+    std::string data;
+    {
+        char buf[1 << 16];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, got);
+        fclose(f);
+    }
+    if (data.empty()) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": empty input (no FASTA/FASTQ record)");
+    if (data[0] != '>' && data[0] != '@')
+        throw Error(SUFR_B200_ERR_IO, std::string(path) + ": not a FASTA/FASTQ file");
+
+    std::vector<uint8_t> seq;
+    seq.reserve(data.size() + 1);
+    std::vector<uint64_t> starts;
+    std::vector<std::string> names;
+    size_t pos = 0;
+    const size_t n = data.size();
+    auto next_line = [&](size_t& b, size_t& e) -> bool {
+        if (pos >= n) return false;
+        b = pos;
+        const void* nl = memchr(data.data() + pos, '\n', n - pos);
+        e = nl ? (size_t)((const char*)nl - data.data()) : n;
+        pos = e + 1;
+        if (e > b && data[e - 1] == '\r') e--;
+        return true;
+    };
+    uint64_t i = 0;
+    auto begin_record = [&](size_t hb, size_t he) {
+        if (i > 0) seq.push_back(delim);     // util.rs:62-64
+        starts.push_back(seq.size());        // util.rs:67
+        i += 1;
+        size_t s = hb;
+        while (s < he && isspace((unsigned char)data[s])) s++;
+        size_t e = s;
+        while (e < he && !isspace((unsigned char)data[e])) e++;
+        names.push_back(e > s ? data.substr(s, e - s) : std::to_string(i + 1));  // util.rs:73-76
+    };
+    size_t b, e;
+    if (data[0] == '>') {
+        while (next_line(b, e)) {
+            if (e > b && data[b] == '>') begin_record(b + 1, e);
+            else seq.insert(seq.end(), data.begin() + b, data.begin() + e);
+        }
+    } else {
+        while (next_line(b, e)) {
+            if (e == b) continue;
+            begin_record(b + 1, e);
+            size_t sb, se, xb, xe;
+            if (!next_line(sb, se) || !next_line(xb, xe) || !next_line(xb, xe))
+                throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated FASTQ record");
+            seq.insert(seq.end(), data.begin() + sb, data.begin() + se);
+        }
+    }
+    seq.push_back('$');  // SENTINEL_CHARACTER, types.rs:20 / util.rs:82
+
+    out->seq_len = seq.size();
+    out->seq = (uint8_t*)malloc(seq.size());
+    memcpy(out->seq, seq.data(), seq.size());
+    out->num_sequences = starts.size();
+    out->start_positions = (uint64_t*)malloc(std::max<size_t>(1, starts.size()) * 8);
+    out->sequence_names = (char**)malloc(std::max<size_t>(1, names.size()) * sizeof(char*));
+    for (size_t k = 0; k < starts.size(); k++) {
+        out->start_positions[k] = starts[k];
+        out->sequence_names[k] = strdup(names[k].c_str());
+    }
+}
+
+void free_sequences(SufrB200Sequences* s) {
+    if (!s) return;
+    free(s->seq);
+    free(s->start_positions);
+    for (uint64_t k = 0; k < s->num_sequences; k++) free(s->sequence_names[k]);
+    free(s->sequence_names);
+    memset(s, 0, sizeof(*s));
+}
+
+}  // namespace sufr

@@ -1,0 +1,525 @@
+// Kernels and scan functors of the build pipeline (everything except the radix sort).
+#pragma once
+#include "common.cuh"
+#include "keys.cuh"
+#include "scan.cuh"
+
+namespace sufr {
+
+constexpr int kBlock = 256;
+
+// scan outputs that only want the grand total
+struct CountOnly {
+    __device__ void operator()(uint64_t, uint32_t, uint32_t) const {}
+};
+struct CountOnlyU64 {
+    __device__ void operator()(uint64_t, unsigned long long, unsigned long long) const {}
+};
+
+inline uint32_t grid_for(uint64_t n, int per_thread = 1) {
+    uint64_t blocks = div_up(n, (uint64_t)kBlock * per_thread);
+    uint64_t cap = (uint64_t)kNumSMs * 32;  // grid-stride beyond 32 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    return (uint32_t)(blocks ? blocks : 1);
+}
+
+// ------------------------------------------------------------------ encode (sufr_builder.rs:144-160)
+// Lowercase ASCII -> 'N' (ignore_softmask) or uppercase; also records which bytes occur.
+__global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __restrict__ in,
+                                                           uint8_t* __restrict__ out, uint64_t n,
+                                                           int ignore_softmask, uint32_t* __restrict__ present) {
+    __shared__ uint32_t seen[256];
+    seen[threadIdx.x] = 0;
+    __syncthreads();
+    const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    const uint64_t nvec = aligned ? n / 16 : 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        uint4 x = reinterpret_cast<const uint4*>(in)[v];
+        uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t c = (w[k] >> (8 * b)) & 0xFF;
+                if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
+                seen[c] = 1;
+                r |= c << (8 * b);
+            }
+            w[k] = r;
+        }
+        reinterpret_cast<uint4*>(out)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t c = in[i];
+        if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
+        seen[c] = 1;
+        out[i] = (uint8_t)c;
+    }
+    __syncthreads();
+    if (seen[threadIdx.x]) present[threadIdx.x] = 1;
+}
+
+// One 64-bit word (K symbols) per thread.
+__global__ void __launch_bounds__(kBlock) pack_kernel(const uint8_t* __restrict__ text, uint64_t n,
+                                                      const uint8_t* __restrict__ code_lut, uint32_t bits,
+                                                      uint32_t K, uint64_t num_words, uint64_t* __restrict__ words) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = code_lut[threadIdx.x];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < num_words; w += stride) {
+        uint64_t base = w * K;
+        uint64_t x = 0;
+        for (uint32_t j = 0; j < K; j++) {
+            uint64_t i = base + j;
+            uint64_t c = i < n ? lut[text[i]] : 0;
+            x |= c << (64 - bits * (j + 1));
+        }
+        words[w] = x;
+    }
+}
+
+// ------------------------------------------------------------------ first key word of every suffix
+// Element e of the sort input is suffix e (full sort) or n-1-e (mask / max-query-len: the stable sort
+// then leaves equal keys in position-descending order, the reference's tie rule, sufr_builder.rs:701-703).
+__global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, int descending,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        uint64_t p = descending ? n - 1 - e : e;
+        keys[e] = key_word(ks, p, 0);
+        pos[e] = (uint32_t)p;
+    }
+}
+
+// Shard selection (multi-GPU): only suffixes whose first key word lies in [lo, hi) belong to this rank.
+struct ShardIn {
+    KeySpec ks;
+    uint64_t n;
+    int descending;
+    uint64_t lo, hi;  // hi == 0 means "no upper bound"
+    __device__ uint32_t operator()(uint64_t e) const {
+        uint64_t p = descending ? n - 1 - e : e;
+        uint64_t k = key_word(ks, p, 0);
+        return (k >= lo && (hi == 0 || k < hi)) ? 1u : 0u;
+    }
+};
+struct ShardOut {
+    KeySpec ks;
+    uint64_t n;
+    int descending;
+    uint64_t* keys;
+    uint32_t* pos;
+    __device__ void operator()(uint64_t e, uint32_t v, uint32_t incl) const {
+        if (v) {
+            uint64_t p = descending ? n - 1 - e : e;
+            keys[incl - 1] = key_word(ks, p, 0);
+            pos[incl - 1] = (uint32_t)p;
+        }
+    }
+};
+
+__device__ __forceinline__ bool indexed_byte(uint8_t c) { return c == '$' || c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// Histogram of the top `hbits` bits of the first key word over the indexed suffixes (splitter selection).
+__global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n, uint32_t hbits,
+                                                          const uint8_t* __restrict__ text, int filter,
+                                                          unsigned long long* __restrict__ hist) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t bins = 1u << hbits;
+    for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+        if (!filter || indexed_byte(text[p])) atomicAdd(&sh[(uint32_t)(key_word(ks, p, 0) >> (64 - hbits))], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// ------------------------------------------------------------------ views of the group structure
+// Round 0 works on the whole sorted array (one segment); later rounds on the compacted "active"
+// elements (members of groups whose keys are still equal), with their segment ids and SA slots.
+struct ViewAll {
+    const uint64_t* key;
+    const uint32_t* pos;
+    __device__ uint64_t k(uint64_t i) const { return key[i]; }
+    __device__ uint32_t p(uint64_t i) const { return pos[i]; }
+    __device__ bool same_seg(uint64_t i) const { return i > 0; }
+    __device__ uint32_t slot(uint64_t i) const { return (uint32_t)i; }
+};
+struct ViewActive {
+    const uint64_t* key;
+    const uint32_t* pos;
+    const uint32_t* seg;
+    const uint32_t* slot_;
+    __device__ uint64_t k(uint64_t i) const { return key[i]; }
+    __device__ uint32_t p(uint64_t i) const { return pos[i]; }
+    __device__ bool same_seg(uint64_t i) const { return i > 0 && seg[i] == seg[i - 1]; }
+    __device__ uint32_t slot(uint64_t i) const { return slot_[i]; }
+};
+
+// After sorting by key word `word`: write the LCP of every newly created group boundary, mark the
+// still-unresolved elements, or (last word of a capped key) close ties.
+template <typename View>
+__global__ void __launch_bounds__(kBlock) resolve_kernel(View v, uint64_t m, KeySpec ks, uint32_t word,
+                                                         int final_word, int is_round0,
+                                                         uint32_t* __restrict__ lcp) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        if (!v.same_seg(i)) {
+            if (is_round0) lcp[v.slot(i)] = 0;  // i == 0
+            continue;                            // segment heads keep the LCP of an earlier round
+        }
+        uint64_t ki = v.k(i), kp = v.k(i - 1);
+        if (ki != kp) {
+            lcp[v.slot(i)] = lcp_from_words(ks, kp, ki, (uint64_t)word * ks.pt.K, v.p(i - 1), v.p(i));
+        } else if (final_word) {
+            uint64_t la = key_len(ks, v.p(i - 1)), lb = key_len(ks, v.p(i));
+            lcp[v.slot(i)] = (uint32_t)(la < lb ? la : lb);
+        } else {
+            lcp[v.slot(i)] = kLcpPending;
+        }
+    }
+}
+
+// Compaction of the elements that are still in a group of size > 1.  Sum-scan input: bit 0 = active,
+// bit 32 = active and first of its group.
+template <typename View>
+struct ActiveIn {
+    View v;
+    uint64_t m;
+    int final_word;
+    __device__ unsigned long long operator()(uint64_t i) const {
+        if (final_word) return 0;
+        uint64_t ki = v.k(i);
+        bool head = !v.same_seg(i) || v.k(i - 1) != ki;
+        bool next_same = (i + 1 < m) && v.same_seg(i + 1) && v.k(i + 1) == ki;
+        bool active = !head || next_same;
+        return active ? (1ull | ((unsigned long long)head << 32)) : 0ull;
+    }
+};
+template <typename View>
+struct ActiveOut {
+    View v;
+    uint32_t* new_slot;
+    uint32_t* new_pos;
+    uint32_t* new_seg;
+    __device__ void operator()(uint64_t i, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            uint32_t a = (uint32_t)incl - 1;
+            new_slot[a] = v.slot(i);
+            new_pos[a] = v.p(i);
+            new_seg[a] = (uint32_t)(incl >> 32) - 1;
+        }
+    }
+};
+
+// Next key word of every active element, packed with (segment, position) as the sort payload.
+__global__ void __launch_bounds__(kBlock) active_keys_kernel(KeySpec ks, uint64_t m, uint32_t word,
+                                                             const uint32_t* __restrict__ pos,
+                                                             const uint32_t* __restrict__ seg,
+                                                             uint64_t* __restrict__ keys,
+                                                             uint64_t* __restrict__ segpos) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
+        uint32_t p = pos[a];
+        keys[a] = key_word(ks, p, word);
+        segpos[a] = ((uint64_t)seg[a] << 32) | p;
+    }
+}
+
+// After the segmented sort: positions go back to their SA slots (the set of slots of a segment is unchanged).
+__global__ void __launch_bounds__(kBlock) writeback_segpos_kernel(uint64_t m, const uint64_t* __restrict__ segpos,
+                                                                  const uint32_t* __restrict__ slot,
+                                                                  uint32_t* __restrict__ pos,
+                                                                  uint32_t* __restrict__ sa) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
+        uint32_t p = (uint32_t)segpos[a];
+        pos[a] = p;
+        sa[slot[a]] = p;
+    }
+}
+__global__ void __launch_bounds__(kBlock) writeback_pos_kernel(uint64_t m, const uint32_t* __restrict__ pos,
+                                                               const uint32_t* __restrict__ slot,
+                                                               uint32_t* __restrict__ sa) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) sa[slot[a]] = pos[a];
+}
+
+// ------------------------------------------------------------------ prefix doubling (deep repeats)
+__global__ void __launch_bounds__(kBlock) isa_init_kernel(uint64_t n, const uint32_t* __restrict__ sa,
+                                                          uint32_t* __restrict__ isa) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) isa[sa[j]] = (uint32_t)j;
+}
+
+// rank of an active element = SA slot of the first element of its group
+struct GroupStartIn {
+    const uint32_t* seg;
+    __device__ uint32_t operator()(uint64_t a) const { return (a == 0 || seg[a] != seg[a - 1]) ? (uint32_t)a : 0u; }
+};
+struct GroupRankOut {
+    const uint32_t* slot;
+    const uint32_t* pos;
+    uint32_t* isa;
+    __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const { isa[pos[a]] = slot[first]; }
+};
+
+// composite key (segment << 32 | rank of suffix p+h, 0 = beyond the end)
+__global__ void __launch_bounds__(kBlock) doubling_keys_kernel(uint64_t m, uint64_t n, uint64_t h,
+                                                               const uint32_t* __restrict__ pos,
+                                                               const uint32_t* __restrict__ seg,
+                                                               const uint32_t* __restrict__ isa,
+                                                               uint64_t* __restrict__ ck) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
+        uint64_t q = (uint64_t)pos[a] + h;
+        uint32_t r = q < n ? isa[q] + 1u : 0u;
+        ck[a] = ((uint64_t)seg[a] << 32) | r;
+    }
+}
+
+struct DoublingStartIn {
+    const uint64_t* ck;
+    __device__ uint32_t operator()(uint64_t a) const { return (a == 0 || ck[a] != ck[a - 1]) ? (uint32_t)a : 0u; }
+};
+// new ranks + lower-bound LCP marks for the boundaries created by this round
+struct DoublingRankOut {
+    const uint64_t* ck;
+    const uint32_t* slot;
+    const uint32_t* pos;
+    uint32_t* isa;
+    uint32_t* lcp;
+    uint32_t mark;  // kLcpLowerBound | min(h, 2^31 - 1)
+    __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const {
+        isa[pos[a]] = slot[first];
+        if (a > 0 && ck[a] != ck[a - 1] && (ck[a] >> 32) == (ck[a - 1] >> 32)) lcp[slot[a]] = mark;
+    }
+};
+struct DoublingActiveIn {
+    const uint64_t* ck;
+    uint64_t m;
+    __device__ unsigned long long operator()(uint64_t a) const {
+        uint64_t c = ck[a];
+        bool head = a == 0 || ck[a - 1] != c;
+        bool next_same = a + 1 < m && ck[a + 1] == c;
+        bool active = !head || next_same;
+        return active ? (1ull | ((unsigned long long)head << 32)) : 0ull;
+    }
+};
+struct DoublingActiveOut {
+    const uint32_t* slot;
+    const uint32_t* pos;
+    uint32_t* new_slot;
+    uint32_t* new_pos;
+    uint32_t* new_seg;
+    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            uint32_t b = (uint32_t)incl - 1;
+            new_slot[b] = slot[a];
+            new_pos[b] = pos[a];
+            new_seg[b] = (uint32_t)(incl >> 32) - 1;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ LCP completion
+// Entries marked kLcpLowerBound|h are computed by direct word-wise comparison from offset h.
+// Pairs that both start inside recorded N runs use the reference's shortcut (sufr_builder.rs:305-307).
+__global__ void __launch_bounds__(kBlock) lcp_complete_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
+                                                              uint32_t* __restrict__ lcp) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+        uint32_t v = lcp[j];
+        if (v == kLcpPending || !(v & kLcpLowerBound) || j == 0) continue;
+        uint64_t pa = sa[j - 1], pb = sa[j];
+        uint64_t ea, eb;
+        if (ks.num_n_ranges && n_run_end(ks, pa, ea) && n_run_end(ks, pb, eb)) {
+            uint64_t ra = ea - pa, rb = eb - pb;
+            lcp[j] = (uint32_t)(ra < rb ? ra : rb);
+            continue;
+        }
+        uint64_t l = lcp_direct(ks, pa, pb, v & ~kLcpLowerBound);
+        if (ks.mode == kModeMaxQueryLen && l > ks.cap) l = ks.cap;
+        lcp[j] = (uint32_t)l;
+    }
+}
+
+// ------------------------------------------------------------------ long runs of N (sufr_builder.rs:174-195)
+struct NRunStartIn {
+    const uint8_t* t;
+    __device__ uint32_t operator()(uint64_t i) const { return (t[i] == 'N' && (i == 0 || t[i - 1] != 'N')) ? 1u : 0u; }
+};
+struct NRunEndIn {
+    const uint8_t* t;
+    __device__ uint32_t operator()(uint64_t i) const { return (i > 0 && t[i] != 'N' && t[i - 1] == 'N') ? 1u : 0u; }
+};
+struct IndexOut {
+    uint64_t* out;
+    __device__ void operator()(uint64_t i, uint32_t v, uint32_t incl) const {
+        if (v) out[incl - 1] = i;
+    }
+};
+struct NRunLongIn {
+    const uint64_t* starts;
+    const uint64_t* ends;
+    uint64_t min_len;
+    __device__ uint32_t operator()(uint64_t k) const { return (ends[k] - starts[k] >= min_len) ? 1u : 0u; }
+};
+struct NRunLongOut {
+    const uint64_t* starts;
+    const uint64_t* ends;
+    uint64_t* out_starts;
+    uint64_t* out_ends;
+    __device__ void operator()(uint64_t k, uint32_t v, uint32_t incl) const {
+        if (v) {
+            out_starts[incl - 1] = starts[k];
+            out_ends[incl - 1] = ends[k];
+        }
+    }
+};
+
+// N-run rule applied to the finished order (full / mql sort with allow_ambiguity): two neighbours that
+// both start in recorded runs have LCP min(r1, r2); if additionally r1 == r2 and the bytes after the
+// runs are equal the reference calls them equal and emits the larger position first
+// (sufr_builder.rs:305-307, 701-712).  Marks such "tie pairs".
+__device__ __forceinline__ bool n_tie_pair(const KeySpec& ks, const uint8_t* text, uint64_t pa, uint64_t pb,
+                                           uint64_t& lcp_out, bool& both) {
+    uint64_t ea, eb;
+    both = n_run_end(ks, pa, ea) && n_run_end(ks, pb, eb);
+    if (!both) return false;
+    uint64_t ra = ea - pa, rb = eb - pb;
+    lcp_out = ra < rb ? ra : rb;
+    return ra == rb && text[ea] == text[eb];
+}
+__global__ void __launch_bounds__(kBlock) n_rule_lcp_kernel(KeySpec ks, const uint8_t* __restrict__ text, uint64_t s,
+                                                            const uint32_t* __restrict__ sa,
+                                                            uint32_t* __restrict__ lcp) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = 1 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+        uint64_t l;
+        bool both;
+        n_tie_pair(ks, text, sa[j - 1], sa[j], l, both);
+        if (both) {
+            if (ks.mode == kModeMaxQueryLen) {
+                // find_lcp ignores max_query_len on this branch (sufr_builder.rs:305-307)
+            }
+            lcp[j] = (uint32_t)l;
+        }
+    }
+}
+struct NTieIn {
+    KeySpec ks;
+    const uint8_t* text;
+    const uint32_t* sa;
+    uint64_t s;
+    __device__ bool tie(uint64_t j) const {  // pair (j-1, j)
+        if (j == 0 || j >= s) return false;
+        uint64_t l;
+        bool both;
+        return n_tie_pair(ks, text, sa[j - 1], sa[j], l, both);
+    }
+    __device__ unsigned long long operator()(uint64_t j) const {
+        bool t0 = tie(j), t1 = tie(j + 1);
+        bool active = t0 || t1;
+        bool head = !t0;
+        return active ? (1ull | ((unsigned long long)head << 32)) : 0ull;
+    }
+};
+struct NTieOut {
+    const uint32_t* sa;
+    uint32_t* new_slot;
+    uint32_t* new_pos;
+    uint64_t* ck;
+    __device__ void operator()(uint64_t j, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            uint32_t a = (uint32_t)incl - 1;
+            uint32_t p = sa[j];
+            new_slot[a] = (uint32_t)j;
+            new_pos[a] = p;
+            ck[a] = ((incl >> 32) - 1) << 32 | (uint32_t)(0xFFFFFFFFu - p);  // position descending
+        }
+    }
+};
+
+// ------------------------------------------------------------------ suffix filter (sufr_builder.rs:446-449)
+
+struct FilterCountIn {
+    const uint8_t* text;
+    const uint32_t* sa;
+    __device__ uint32_t operator()(uint64_t j) const { return indexed_byte(text[sa[j]]) ? 1u : 0u; }
+};
+struct FilterSaOut {
+    const uint32_t* sa;
+    uint32_t* out_sa;
+    uint32_t* kept_index;  // compacted index -> original index
+    __device__ void operator()(uint64_t j, uint32_t v, uint32_t incl) const {
+        if (v) {
+            out_sa[incl - 1] = sa[j];
+            kept_index[incl - 1] = (uint32_t)j;
+        }
+    }
+};
+// LCP of two kept neighbours = min over the skipped stretch.  Values are ordered by (value, is-lower-bound)
+// so that an exact value wins over an equal lower bound; segments restart after every kept element.
+__device__ __forceinline__ uint32_t lcp_to_ord(uint32_t v) {
+    return (v & kLcpLowerBound) ? (((v & ~kLcpLowerBound) << 1) | 1u) : (v << 1);
+}
+__device__ __forceinline__ uint32_t ord_to_lcp(uint32_t o) { return (o & 1u) ? ((o >> 1) | kLcpLowerBound) : (o >> 1); }
+struct FilterLcpIn {
+    const uint8_t* text;
+    const uint32_t* sa;
+    const uint32_t* lcp;
+    __device__ unsigned long long operator()(uint64_t j) const {
+        unsigned long long restart = (j == 0 || indexed_byte(text[sa[j - 1]])) ? 1ull : 0ull;
+        return (restart << 32) | lcp_to_ord(lcp[j]);
+    }
+};
+struct FilterLcpOut {
+    const uint8_t* text;
+    const uint32_t* sa;
+    const uint32_t* excl_count;  // unused
+    uint32_t* scanned;           // per original index: min over its stretch
+    __device__ void operator()(uint64_t j, unsigned long long, unsigned long long incl) const {
+        scanned[j] = ord_to_lcp((uint32_t)incl);
+    }
+};
+__global__ void __launch_bounds__(kBlock) gather_u32_kernel(uint64_t m, const uint32_t* __restrict__ idx,
+                                                            const uint32_t* __restrict__ src,
+                                                            uint32_t* __restrict__ dst) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) dst[a] = src[idx[a]];
+}
+
+__global__ void __launch_bounds__(kBlock) widen_kernel(uint64_t m, const uint32_t* __restrict__ src,
+                                                       unsigned long long* __restrict__ dst) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) dst[a] = src[a];
+}
+
+// ------------------------------------------------------------------ synthetic workloads (bench.py)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// base i = "ACGT"[top 2 bits of splitmix64(seed, i)]
+__global__ void __launch_bounds__(kBlock) synth_dna_kernel(uint8_t* __restrict__ text, uint64_t n, uint64_t seed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t z = mix64(seed * 0x9E3779B97F4A7C15ull + (i + 1) * 0x9E3779B97F4A7C15ull);
+        text[i] = (uint8_t)("ACGT"[z >> 62]);
+    }
+}
+__global__ void synth_marks_kernel(uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ starts,
+                                   uint64_t num, uint8_t delim) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 1 && k < num && starts[k] >= 1 && starts[k] - 1 < n) text[starts[k] - 1] = delim;
+    if (k == 0 && n) text[n - 1] = '$';
+}
+
+}  // namespace sufr

@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden files.
+Bit-exact: SA, LCP, transformed text, and the whole `.sufr` file."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_CASES
+import oracle as O
+from sufrfile import parse_sufr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sufr_b200
+    return sufr_b200
+
+
+def gpu_vs_oracle(S, text, index_bits=32, **kw):
+    want = O.oracle_build(text, num_partitions=kw.pop("oracle_partitions", 16), threads=4,
+                          index_bits=index_bits, **kw)
+    got = S.build(S.SufrBuilderArgs(text=text, **kw), index_bits=index_bits)
+    try:
+        assert got.text == want.text
+        assert got.num_suffixes == want.num_suffixes
+        sa, lcp = got.sa.copy(), got.lcp.copy()
+        assert sa.dtype == want.sa.dtype
+        if not np.array_equal(sa, want.sa):
+            bad = int(np.nonzero(sa != want.sa)[0][0])
+            raise AssertionError(f"SA differs first at rank {bad}: got {sa[bad:bad+5]} want {want.sa[bad:bad+5]}")
+        if not np.array_equal(lcp, want.lcp):
+            bad = int(np.nonzero(lcp != want.lcp)[0][0])
+            raise AssertionError(f"LCP differs first at rank {bad}: got {lcp[bad:bad+5]} want {want.lcp[bad:bad+5]} "
+                                 f"(sa {sa[max(0,bad-1):bad+1]})")
+        assert got.n_ranges == want.n_ranges
+        return got.timings, got.c.refine_rounds, got.c.doubling_rounds
+    finally:
+        got.free()
+
+
+@pytest.mark.parametrize("golden,fasta,flags", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_golden_whole_file(S, tmp_path, golden, fasta, flags):
+    """The reference's own create tests (sufr/tests/cli.rs:113-302) compare the SA; we compare the file."""
+    flags = dict(flags)
+    delim = flags.pop("delimiter", b"%")
+    seq = S.read_sequence_file(GOLDEN / "inputs" / fasta, delim)
+    out = tmp_path / golden
+    b = S.SufrBuilder(S.SufrBuilderArgs(text=seq.seq, path=str(out), sequence_starts=seq.start_positions,
+                                        sequence_names=seq.sequence_names, **flags), 32)
+    want = (GOLDEN / "expected" / golden).read_bytes()
+    g = parse_sufr(want)
+    assert b.text == g.text
+    np.testing.assert_array_equal(b.suffix_array, g.sa)
+    np.testing.assert_array_equal(b.lcp_array, g.lcp)
+    assert out.read_bytes() == want
+    assert b.num_suffixes == g.num_suffixes
+
+
+def test_lib_rs_vectors(S):
+    # libsufr/src/lib.rs:45-92 (u32) and :94-140 (u64)
+    d = S.read_sequence_file(GOLDEN / "inputs" / "2.fa", b"N")
+    r = S.build(S.SufrBuilderArgs(text=d.seq, is_dna=True, num_partitions=2, random_seed=0), index_bits=32)
+    assert r.text == b"ACGTACGTNACGTACGT$"
+    assert r.sa.tolist() == [17, 13, 9, 0, 4, 14, 10, 1, 5, 15, 11, 2, 6, 16, 12, 3, 7]
+    assert r.lcp.tolist() == [0, 0, 4, 8, 4, 0, 3, 7, 3, 0, 2, 6, 2, 0, 1, 5, 1]
+    d = S.read_sequence_file(GOLDEN / "inputs" / "1.fa", b"N")
+    r = S.build(S.SufrBuilderArgs(text=d.seq, is_dna=True, allow_ambiguity=True, num_partitions=2, random_seed=0),
+                index_bits=64)
+    assert r.sa.dtype == np.uint64
+    assert r.sa.tolist() == [10, 6, 0, 7, 1, 8, 2, 5, 4, 9, 3]
+    assert r.lcp.tolist() == [0, 0, 4, 0, 3, 0, 2, 0, 1, 0, 1]
+
+
+@pytest.mark.parametrize("fasta,mask,want", [
+    ("mostlya1.fa", "101", [7, 6, 5, 4, 2, 0, 1, 3]),
+    ("mostlya2.fa", "11011", [16, 13, 9, 5, 1, 12, 8, 4, 0, 14, 10, 6, 2, 15, 11, 7, 3]),
+    ("spaced_input.fa", "11000111",
+     [42, 18, 12, 0, 32, 29, 13, 23, 21, 6, 40, 1, 33, 19, 30, 10, 28, 9, 17, 14, 4, 26, 39, 22, 25, 38, 24,
+      35, 7, 36, 15, 41, 5, 20, 31, 11, 27, 8, 16, 3, 37, 34, 2]),
+])
+def test_lib_rs_spaced_seeds(S, fasta, mask, want):
+    # libsufr/src/lib.rs:221-365: pins the position-descending tie order
+    d = S.read_sequence_file(GOLDEN / "inputs" / fasta, b"N")
+    r = S.build(S.SufrBuilderArgs(text=d.seq, is_dna=True, num_partitions=1, random_seed=0, seed_mask=mask))
+    assert r.sa.tolist() == want
+
+
+def rand_text(rng, n, alphabet, repeat_p=0.0, max_rep=40):
+    out = bytearray()
+    while len(out) < n:
+        if out and rng.random() < repeat_p:
+            s = rng.randrange(len(out))
+            ln = rng.randrange(1, max_rep)
+            out += out[s:s + ln]
+        else:
+            out.append(rng.choice(alphabet))
+    return bytes(out[:n]) + b"$"
+
+
+ALPHABETS = {
+    "acgt": (b"ACGT", dict(is_dna=True)),
+    "dna_mixed": (b"ACGTNacgtn%RY", dict(is_dna=True)),
+    "dna_amb": (b"ACGTNacgtn%RY", dict(is_dna=True, allow_ambiguity=True)),
+    "dna_soft": (b"ACGTNacgtn%", dict(is_dna=True, ignore_softmask=True)),
+    "dna_amb_soft": (b"ACGTNacgtn%", dict(is_dna=True, allow_ambiguity=True, ignore_softmask=True)),
+    "protein": (b"ACDEFGHIKLMNPQRSTVWY%", dict()),
+    "binary": (b"AB", dict()),
+    "bytes": (bytes(range(1, 36)) + bytes(range(128, 250)), dict()),
+}
+
+
+@pytest.mark.parametrize("name", list(ALPHABETS))
+@pytest.mark.parametrize("n", [1, 2, 5, 63, 64, 65, 1000, 30000])
+def test_full_sort_random(S, name, n):
+    alphabet, flags = ALPHABETS[name]
+    rng = random.Random(hash((name, n)) & 0xFFFFFF)
+    text = rand_text(rng, n, alphabet, repeat_p=0.05)
+    if n <= 2:
+        text = text[:-1] + b"$$$"[: 4 - n]  # the reference needs text_len >= 4 (partition count n/4)
+    gpu_vs_oracle(S, text, **flags)
+
+
+@pytest.mark.parametrize("mask", ["101", "1101", "11011", "10111011", "1101101101", "111010010100110111",
+                                  "1" * 20 + "0" + "1" * 20])
+@pytest.mark.parametrize("name", ["acgt", "dna_amb", "protein", "binary"])
+def test_seed_mask_random(S, mask, name):
+    alphabet, flags = ALPHABETS[name]
+    rng = random.Random(hash((mask, name)) & 0xFFFFFF)
+    text = rand_text(rng, rng.randrange(50, 20000), alphabet, repeat_p=0.05)
+    gpu_vs_oracle(S, text, seed_mask=mask, **flags)
+
+
+def test_text_without_sentinel(S):
+    # library users may pass a text without a trailing '$' (sufr_builder.rs:1044, 1086)
+    for t in (b"TTTAGC", b"ACGTNNACGT", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"):
+        gpu_vs_oracle(S, t)
+        gpu_vs_oracle(S, t, seed_mask="101")
+
+
+@pytest.mark.parametrize("unit,copies", [(b"A", 3000), (b"AC", 2500), (b"ACGGT", 1500), (b"ACGTTGCATTGACCA", 700)])
+def test_tandem_repeats_use_prefix_doubling(S, unit, copies):
+    """Long-LCP worst case (BASELINE config 5 flavour): deep repeats switch to prefix doubling."""
+    rng = random.Random(len(unit))
+    text = rand_text(rng, 500, b"ACGT") [:-1] + unit * copies + rand_text(rng, 300, b"ACGT")[:-1] + unit * (copies // 2) + b"$"
+    _, _, doubling = gpu_vs_oracle(S, text, is_dna=True)
+    assert doubling > 0
+    gpu_vs_oracle(S, text, is_dna=True, index_bits=64)
+
+
+def n_run_text(rng, runs, filler=400):
+    parts = []
+    for r in runs:
+        parts.append(rand_text(rng, rng.randrange(50, filler), b"ACGT")[:-1])
+        parts.append(b"N" * r)
+    parts.append(rand_text(rng, 200, b"ACGT")[:-1])
+    return b"".join(parts) + b"$"
+
+
+@pytest.mark.parametrize("runs", [[1000], [999], [2000], [1500, 1500, 1200, 3000], [1000, 1000, 1000, 1000, 1000, 1000]])
+@pytest.mark.parametrize("soft", [False, True])
+def test_long_n_runs_allow_ambiguity(S, runs, soft):
+    """SURVEY 8a rule 3: every N-prefixed suffix lies in a recorded (>= 1000) run, or there is a single
+    short run, so the reference result is a function of the input."""
+    rng = random.Random(sum(runs) + soft)
+    text = n_run_text(rng, runs)
+    if soft:
+        text = text.replace(b"N", b"n")
+    gpu_vs_oracle(S, text, is_dna=True, allow_ambiguity=True, ignore_softmask=soft)
+    # same text without --allow-ambiguity: N starts are filtered out, LCPs span the removed stretch
+    gpu_vs_oracle(S, text, is_dna=True, ignore_softmask=soft)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_max_query_len_without_ties(S, seed):
+    rng = random.Random(seed)
+    text = rand_text(rng, 5000, b"ACDEFGHIKLMNPQRSTVWY")
+    full = O.oracle_build(text, num_partitions=4)
+    q = int(full.lcp.max()) + 1
+    gpu_vs_oracle(S, text, max_query_len=q)
+    gpu_vs_oracle(S, text, max_query_len=q + 100)
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 7, 12, 13, 40])
+def test_max_query_len_with_ties_properties(S, q):
+    """With ties the reference output depends on its merge schedule (SURVEY 8a rule 4); what is defined:
+    the first Q bytes are non-decreasing, LCP values < Q are exact, the others are >= Q (we emit exactly Q
+    and order ties by descending position)."""
+    rng = random.Random(q)
+    text = rand_text(rng, 20000, b"ACGT", repeat_p=0.1)
+    got = S.build(S.SufrBuilderArgs(text=text, max_query_len=q))
+    sa, lcp = got.sa.copy(), got.lcp.copy()
+    t, spec_sa, spec_lcp = O.spec_build(text, max_query_len=q)
+    assert sa.tolist() == spec_sa
+    assert lcp.tolist() == spec_lcp
+    ref = O.oracle_build(text, max_query_len=q, num_partitions=4)
+    small = ref.lcp < q
+    keys_ref = [t[p:p + q] for p in ref.sa.tolist()]
+    keys_got = [t[p:p + q] for p in sa.tolist()]
+    assert keys_ref == keys_got
+    assert np.array_equal(lcp[small], ref.lcp[small])
+    assert (lcp[~small] == q).all() and (ref.lcp[~small] >= q).all()
+
+
+def test_argument_errors(S):
+    # same message texts as the reference (sufr_builder.rs:163-165, types.rs:81-83)
+    with pytest.raises(S.SufrError, match="Cannot use max_query_len and seed_mask together"):
+        S.build(S.SufrBuilderArgs(text=b"ACGT$", max_query_len=3, seed_mask="101"))
+    with pytest.raises(S.SufrError, match="Invalid seed mask '111'"):
+        S.build(S.SufrBuilderArgs(text=b"ACGT$", seed_mask="111"))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("kw", [dict(is_dna=True), dict(is_dna=True, seed_mask="1101101101"), dict(),
+                                dict(is_dna=True, allow_ambiguity=True)], ids=["dna", "mask", "protein", "amb"])
+def test_key_range_shards_concatenate(S, world, kw):
+    """Multi-GPU decomposition, emulated on one device: shard r of `world` for every r, seams repaired,
+    concatenation == the unsharded oracle result."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = random.Random(world)
+    alphabet = b"ACDEFGHIKLMNPQRSTVWY%" if not kw else b"ACGTN%"
+    text = rand_text(rng, 50000, alphabet, repeat_p=0.03)
+    want = O.oracle_build(text, num_partitions=16, threads=4, **kw)
+    shards = [S.build(S.SufrBuilderArgs(text=text, **kw), rank=r, world_size=world) for r in range(world)]
+    meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+    offs, total = shard_layout(meta)
+    assert total == want.num_suffixes
+    for r, s in enumerate(shards):
+        assert s.total_suffixes == total and s.shard_offset == offs[r]
+        prev = previous_last_suffix(meta, r)
+        if prev is not None and s.num_suffixes:
+            s.patch_seam(prev)
+    sa = np.concatenate([s.sa for s in shards])
+    lcp = np.concatenate([s.lcp for s in shards])
+    assert np.array_equal(sa, want.sa)
+    assert np.array_equal(lcp, want.lcp)
+    assert sum(1 for s in shards if s.num_suffixes) >= min(world, 2)
+
+
+def test_device_resident_result_and_text(S):
+    """The bench's device-resident path: text already in HBM, SA/LCP left in HBM."""
+    import torch
+    rng = np.random.default_rng(3)
+    text = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 300000)].tobytes() + b"$"
+    want = O.oracle_build(text, is_dna=True, threads=4)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    for bits, tdt in ((32, torch.int32), (64, torch.int64)):
+        r = S.build(S.SufrBuilderArgs(text=b"", is_dna=True), index_bits=bits, result_memory=S.MEM_DEVICE,
+                    device_text=(d_text.data_ptr(), d_text.numel()))
+        assert r.on_device and r.num_suffixes == want.num_suffixes
+        sa = r.sa_tensor().cpu().numpy().astype(np.uint64) & (0xFFFFFFFF if bits == 32 else 0xFFFFFFFFFFFFFFFF)
+        lcp = r.lcp_tensor().cpu().numpy().astype(np.uint64) & (0xFFFFFFFF if bits == 32 else 0xFFFFFFFFFFFFFFFF)
+        assert bytes(r.text_tensor().cpu().numpy().tobytes()) == want.text
+        assert np.array_equal(sa, want.sa.astype(np.uint64))
+        assert np.array_equal(lcp, want.lcp.astype(np.uint64))
+        r.free()
