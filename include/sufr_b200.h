@@ -78,6 +78,10 @@ typedef struct SufrB200Timings {
     double finish_ms;     /* N-run tie rule, suffix filter, widening          (:446-449, :305-307) */
     double d2h_ms;        /* device -> host copy of text / SA / LCP (0 for device results) */
     double total_ms;      /* first kernel to last kernel, excluding h2d/d2h */
+    /* The dominant kernel (radix-sort downsweep of the main sort), timed per launch with CUDA events: */
+    double dominant_kernel_ms;        /* sum over its launches in this build */
+    uint64_t dominant_kernel_launches;
+    uint64_t dominant_kernel_bytes;   /* algorithmic bytes of ONE launch: elements x 2 x (8 B key + 4 B position) */
 } SufrB200Timings;
 
 typedef struct SufrB200Result {

@@ -51,7 +51,8 @@ class Args(C.Structure):
 class Timings(C.Structure):
     """struct SufrB200Timings"""
     _fields_ = [(k, C.c_double) for k in
-                ("h2d_ms", "encode_ms", "keys_ms", "sort_ms", "refine_ms", "lcp_ms", "finish_ms", "d2h_ms", "total_ms")]
+                ("h2d_ms", "encode_ms", "keys_ms", "sort_ms", "refine_ms", "lcp_ms", "finish_ms", "d2h_ms", "total_ms",
+                 "dominant_kernel_ms")] + [("dominant_kernel_launches", C.c_uint64), ("dominant_kernel_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -273,6 +273,9 @@ class BuildResult:
 
     def free(self):
         if self.c.owner:
+            if not self._ctx.handle:  # context already destroyed (interpreter shutdown): nothing left to return to
+                self.c.owner = None
+                return
             _lib.lib().sufr_b200_result_free(self._ctx.handle, C.byref(self.c))
 
     def __del__(self):

@@ -13,6 +13,7 @@
 // The oracle (oracle/) is never linked or called from here.
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -31,10 +32,57 @@ namespace sufr {
 
 thread_local std::string g_last_error;
 
+// Pinned host buffers are expensive to allocate (page-locking tens of GB takes seconds), so host results
+// hand their buffers back to the context for the next build.
+struct PinnedCache {
+    std::vector<std::pair<void*, size_t>> free_list;
+    void* get(size_t bytes) {
+        if (bytes == 0) bytes = 1;
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].second >= bytes && (best == (size_t)-1 || free_list[i].second < free_list[best].second)) best = i;
+        if (best != (size_t)-1 && free_list[best].second <= 2 * bytes + (1u << 20)) {
+            void* p = free_list[best].first;
+            sizes[p] = free_list[best].second;
+            free_list.erase(free_list.begin() + best);
+            return p;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            release();
+            e = cudaMallocHost(&p, bytes);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, "cudaMallocHost(" + std::to_string(bytes) + " bytes) failed");
+            }
+        }
+        sizes[p] = bytes;
+        return p;
+    }
+    void put(void* p) {
+        auto it = sizes.find(p);
+        if (it == sizes.end()) { cudaFreeHost(p); return; }
+        free_list.push_back({p, it->second});
+        sizes.erase(it);
+        while (free_list.size() > 6) {  // keep a couple of builds' worth
+            cudaFreeHost(free_list.front().first);
+            free_list.erase(free_list.begin());
+        }
+    }
+    void release() {
+        for (auto& f : free_list) cudaFreeHost(f.first);
+        free_list.clear();
+    }
+    std::map<void*, size_t> sizes;  // buffers currently lent out
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevicePool pool;
+    PinnedCache pinned;
     uint64_t launches = 0;
     std::mutex mu;
 };
@@ -107,6 +155,8 @@ class Build {
     DevBuf<uint32_t> d_counts;  // radix sort count matrix
     uint64_t shard_offset = 0, total_suffixes = 0;
     int t_keys_mark = -1;
+    rsort::EventPairs downsweep_events;
+    uint64_t sorted_elements = 0;
 
     template <typename T>
     DevBuf<T> dalloc(size_t count) { return DevBuf<T>(ctx.pool, count ? count : 1); }
@@ -281,7 +331,8 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted) {
     d_counts = dalloc<uint32_t>(rsort::counts_words());
     const int used = (int)(ks.pt.K * ks.pt.bits);
     bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), s, 64 - used,
-                                                      64, d_counts.get(), st(), &ctx.launches);
+                                                      64, d_counts.get(), st(), &ctx.launches, &downsweep_events);
+    sorted_elements = s;
     if (in_b) {
         keys_sorted = std::move(keys_b);
         d_sa = std::move(pos_b);
@@ -502,7 +553,7 @@ void Build::run(SufrB200Result* out) {
     const uint64_t launches0 = ctx.launches;
     // working set: text n, packed <= n, keys 2x8n, positions 2x4n, lcp 4n (+ output widening 16n for u64)
     {
-        uint64_t per = 30 + (index_bits_ == 64 ? 16 : 0);
+        uint64_t per = 30;  // the u64 widening happens after the key buffers are gone
         uint64_t shard_n = args.world_size > 1 ? n / args.world_size + n / 8 : n;
         ctx.pool.reserve((size_t)(2 * n + per * shard_n + (64ull << 20)));
     }
@@ -596,6 +647,16 @@ void Build::run(SufrB200Result* out) {
     tm.finish_ms = timer.ms(t3, t4) + timer.ms(t5, t6);
     tm.lcp_ms = timer.ms(t4, t5);
     tm.total_ms = timer.ms(t0, t6);
+    for (auto& ev : downsweep_events) {
+        float t = 0;
+        SUFR_CUDA_CHECK(cudaEventElapsedTime(&t, ev.first, ev.second));
+        tm.dominant_kernel_ms += t;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    tm.dominant_kernel_launches = downsweep_events.size();
+    tm.dominant_kernel_bytes = sorted_elements * 2 * (sizeof(uint64_t) + sizeof(uint32_t));
+    downsweep_events.clear();
 
     if (result_memory_ == SUFR_B200_MEM_DEVICE) {
         owner->text = d_text.release();
@@ -608,9 +669,9 @@ void Build::run(SufrB200Result* out) {
         }
     } else {
         int e0 = timer.mark();
-        SUFR_CUDA_CHECK(cudaMallocHost(&owner->text, n ? n : 1));
-        SUFR_CUDA_CHECK(cudaMallocHost(&owner->sa, s ? s * w : 1));
-        SUFR_CUDA_CHECK(cudaMallocHost(&owner->lcp, s ? s * w : 1));
+        owner->text = ctx.pinned.get(n);
+        owner->sa = ctx.pinned.get(s * w);
+        owner->lcp = ctx.pinned.get(s * w);
         int e1 = timer.mark();
         if (n) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
         if (s) {
@@ -660,6 +721,11 @@ static void free_owner(ResultOwner* o) {
             if (o->sa) o->ctx->pool.free(o->sa);
             if (o->lcp) o->ctx->pool.free(o->lcp);
         }
+    } else if (o->ctx) {
+        std::lock_guard<std::mutex> lock(o->ctx->mu);
+        if (o->text) o->ctx->pinned.put(o->text);
+        if (o->sa) o->ctx->pinned.put(o->sa);
+        if (o->lcp) o->ctx->pinned.put(o->lcp);
     } else {
         if (o->text) cudaFreeHost(o->text);
         if (o->sa) cudaFreeHost(o->sa);
@@ -738,6 +804,7 @@ void sufr_b200_ctx_destroy(SufrB200Ctx* c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->pool.release_all();
+    ctx->pinned.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -748,7 +815,8 @@ int sufr_b200_ctx_reserve(SufrB200Ctx* c, uint64_t text_len, uint32_t index_bits
         if (!ctx) throw Error(SUFR_B200_ERR_ARGUMENT, "ctx is NULL");
         std::lock_guard<std::mutex> lock(ctx->mu);
         SUFR_CUDA_CHECK(cudaSetDevice(ctx->device));
-        uint64_t per = 32 + (index_bits == 64 ? 16 : 0);
+        uint64_t per = 32;
+        (void)index_bits;
         ctx->pool.reserve((size_t)(per * text_len + (64ull << 20)));
     });
 }
@@ -759,6 +827,7 @@ void sufr_b200_ctx_trim(SufrB200Ctx* c) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     cudaSetDevice(ctx->device);
     ctx->pool.trim();
+    ctx->pinned.release();
 }
 
 int sufr_b200_build(SufrB200Ctx* c, const SufrB200Args* args, uint32_t index_bits, int text_memory, int result_memory,
@@ -889,8 +958,10 @@ int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out) 
             cudaStreamDestroy(ctx->stream);
             throw;
         }
-        // host result does not need the context any more
+        // host result does not need the context any more (its pinned buffers are freed with cudaFreeHost)
         static_cast<ResultOwner*>(res->owner)->ctx = nullptr;
+        ctx->pinned.sizes.clear();
+        ctx->pinned.release();
         ctx->pool.release_all();
         cudaStreamDestroy(ctx->stream);
     });

@@ -10,6 +10,9 @@
 // Algorithmic bytes per pass and element: sizeof(K) (upsweep read) + 2*(sizeof(K)+sizeof(V))
 // (downsweep read + write).
 #pragma once
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace sufr {
@@ -246,9 +249,12 @@ inline size_t counts_words() { return (size_t)RADIX * kNumSMs * 4; }
 // Sorts on key bits [begin_bit, end_bit).  Buffers ping-pong; returns true when the sorted data ended
 // up in (keys_b, vals_b).  `counts` needs counts_words() u32.  `launches` (optional) is incremented
 // by the number of kernels launched.
+using EventPairs = std::vector<std::pair<cudaEvent_t, cudaEvent_t>>;
+
 template <typename K, typename V>
 bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begin_bit, int end_bit,
-                uint32_t* counts, cudaStream_t stream, uint64_t* launches = nullptr) {
+                uint32_t* counts, cudaStream_t stream, uint64_t* launches = nullptr,
+                EventPairs* downsweep_events = nullptr) {
     constexpr int IPT = Tuning<K, V>::IPT;
     if (n == 0 || end_bit <= begin_bit) return false;
     Plan p = make_plan<K, V>(n);
@@ -264,9 +270,19 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
         SUFR_KERNEL_CHECK();
         scan_counts_kernel<<<1, 1024, 0, stream>>>(counts, (uint32_t)RADIX * p.grid);
         SUFR_KERNEL_CHECK();
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (downsweep_events) {
+            SUFR_CUDA_CHECK(cudaEventCreate(&e0));
+            SUFR_CUDA_CHECK(cudaEventCreate(&e1));
+            SUFR_CUDA_CHECK(cudaEventRecord(e0, stream));
+        }
         downsweep_kernel<K, V, IPT><<<p.grid, BLOCK, 0, stream>>>(kin, kout, vin, vout, n, bit, dmask, counts,
                                                                  p.tiles_per_block);
         SUFR_KERNEL_CHECK();
+        if (downsweep_events) {
+            SUFR_CUDA_CHECK(cudaEventRecord(e1, stream));
+            downsweep_events->push_back({e0, e1});
+        }
         if (launches) *launches += 3;
         in_b = !in_b;
     }

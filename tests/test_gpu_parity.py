@@ -255,3 +255,32 @@ def test_device_resident_result_and_text(S):
         assert np.array_equal(sa, want.sa.astype(np.uint64))
         assert np.array_equal(lcp, want.lcp.astype(np.uint64))
         r.free()
+
+
+def test_bench_workload_generator_matches_cpu_restatement(S):
+    """bench.py's synthetic text: GPU kernel == numpy restatement (the CPU baseline runs on a prefix)."""
+    import torch
+    import bench
+    from sufr_b200 import _lib
+    text_len, starts = bench.record_layout(3_000_000)
+    ctx = S.default_context(0)
+    d = torch.empty(text_len, dtype=torch.uint8, device="cuda")
+    st = np.asarray(starts, dtype=np.uint64)
+    assert _lib.lib().sufr_b200_synth_dna(ctx.handle, d.data_ptr(), text_len, bench.SEED, st.ctypes.data, len(st),
+                                          ord("%")) == 0
+    got = d.cpu().numpy().tobytes()
+    assert got == bench.synth_prefix_numpy(text_len, text_len, starts)
+    assert got.count(b"%") == 23 and got.endswith(b"$")
+
+
+@pytest.mark.parametrize("n", [10_000_000])
+def test_config1_10mbp_random_dna(S, n):
+    """BASELINE configs[0]: `sufr create --dna -n 16` on 10 Mbp random ACGT, u32 -- bit-exact vs the oracle."""
+    rng = np.random.default_rng(1)
+    text = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].tobytes() + b"$"
+    want = O.oracle_build(text, is_dna=True, num_partitions=16, threads=16)
+    got = S.build(S.SufrBuilderArgs(text=text, is_dna=True, num_partitions=16))
+    assert got.num_suffixes == n + 1
+    assert np.array_equal(got.sa, want.sa)
+    assert np.array_equal(got.lcp, want.lcp)
+    got.free()
