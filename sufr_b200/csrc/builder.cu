@@ -120,6 +120,10 @@ struct EventTimer {
     }
 };
 
+// Thrown when prefix doubling is needed but this attempt sorts only a subset of the positions (suffix
+// filter applied up front, or one key-range shard): the build is redone over all positions.
+struct NeedFullSort {};
+
 // ---------------------------------------------------------------------------------------------
 class Build {
    public:
@@ -153,8 +157,9 @@ class Build {
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
     DevBuf<uint32_t> d_counts;  // radix sort count matrix
-    uint64_t shard_offset = 0, total_suffixes = 0;
-    int t_keys_mark = -1;
+    uint64_t shard_offset = 0, shard_count = 0, total_suffixes = 0;
+    bool full_set_ = true;  // every text position is being sorted on this rank (prefix doubling needs that)
+    int t_keys_mark = -1, t_sorted_mark = -1;
     rsort::EventPairs downsweep_events;
     uint64_t sorted_elements = 0;
 
@@ -176,7 +181,8 @@ class Build {
 
     void encode(const uint8_t* d_raw);
     void find_n_runs();
-    void make_keys_and_sort(DevBuf<uint64_t>& keys_sorted);
+    void make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bool sharded);
+    void sort_phase(bool prefilter, bool sharded);
     void refine(DevBuf<uint64_t>& keys_sorted);
     void doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
                   uint64_t h);
@@ -268,7 +274,7 @@ void Build::find_n_runs() {
     }
 }
 
-void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted) {
+void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bool sharded) {
     const int descending = ks.mode != kModeFull;
     const int world = args.world_size > 1 ? args.world_size : 1;
     uint64_t lo = 0, hi = 0;
@@ -302,6 +308,8 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted) {
         uint32_t b0 = cut[args.rank], b1 = cut[args.rank + 1];
         total_suffixes = total;
         for (uint32_t b = 0; b < b0; b++) shard_offset += hist[b];
+        shard_count = 0;
+        for (uint32_t b = b0; b < b1; b++) shard_count += hist[b];
         lo = (uint64_t)b0 << (64 - hbits);
         hi = b1 >= bins ? 0 : (uint64_t)b1 << (64 - hbits);
         if (b0 >= b1) { lo = ~0ull; hi = ~0ull; }  // empty shard: [max, max) selects nothing
@@ -309,12 +317,12 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted) {
 
     DevBuf<uint64_t> keys_a, keys_b;
     DevBuf<uint32_t> pos_a, pos_b;
-    if (world > 1) {
-        ShardIn in{ks, n, descending, lo, hi};
+    if (sharded || prefilter) {
+        SelectIn in{ks, n, descending, sharded ? 1 : 0, lo, hi, d_text.get(), prefilter ? 1 : 0};
         s = scan_total(n, in, scan::SumU32{}, CountOnly{});
         keys_a = dalloc<uint64_t>(s);
         pos_a = dalloc<uint32_t>(s);
-        if (s) scan_total(n, in, scan::SumU32{}, ShardOut{ks, n, descending, keys_a.get(), pos_a.get()});
+        if (s) scan_total(n, in, scan::SumU32{}, SelectOut{ks, n, descending, keys_a.get(), pos_a.get()});
     } else {
         s = n;
         keys_a = dalloc<uint64_t>(s);
@@ -442,9 +450,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
 // Needs the rank of EVERY text position, hence only valid when all positions were sorted on this rank.
 void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
                      uint64_t h) {
-    if (s != n)
-        throw Error(SUFR_B200_ERR_UNSUPPORTED,
-                    "text has repeats deeper than the word-refinement limit; prefix doubling needs an unsharded build");
+    if (!full_set_) throw NeedFullSort{};
     auto isa = dalloc<uint32_t>(n);
     isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa.get());
     SUFR_KERNEL_CHECK();
@@ -522,6 +528,14 @@ void Build::apply_filter() {
     s = kept;
 }
 
+void Build::sort_phase(bool prefilter, bool sharded) {
+    full_set_ = !prefilter && !sharded;
+    DevBuf<uint64_t> keys_sorted;
+    make_keys_and_sort(keys_sorted, prefilter, sharded);
+    t_sorted_mark = timer.mark();
+    refine(keys_sorted);
+}
+
 void Build::run(SufrB200Result* out) {
     n = args.text_len;
     if (n >= 0xFFFFFFFFull)
@@ -585,16 +599,30 @@ void Build::run(SufrB200Result* out) {
     find_n_runs();
     int t1 = timer.mark();
 
-    DevBuf<uint64_t> keys_sorted;
-    make_keys_and_sort(keys_sorted);
-    int t2 = timer.mark();
-    refine(keys_sorted);
-    keys_sorted.reset();
+    // First attempt sorts only what this rank outputs (indexed suffixes of its key range).  Texts with
+    // repeats deeper than the word-refinement limit need the ranks of ALL positions: redo unfiltered and
+    // unsharded, filter afterwards, and cut this rank's slice out of the global result.
+    bool prefilter = filter_active, sharded = args.world_size > 1, sliced = false;
+    try {
+        sort_phase(prefilter, sharded);
+    } catch (const NeedFullSort&) {
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        d_sa.reset();
+        d_lcp.reset();
+        refine_rounds = doubling_rounds = 0;
+        for (auto& ev : downsweep_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+        downsweep_events.clear();
+        sliced = sharded;
+        prefilter = false;
+        sharded = false;
+        ctx.pool.reserve((size_t)(32 * n + (64ull << 20)));
+        sort_phase(false, false);
+    }
+    int t2 = t_sorted_mark;
     int t3 = timer.mark();
 
-    // finish: filter first (so that deep LCPs between non-indexed suffixes are never computed), then the
-    // remaining lower-bound LCP marks, then the N-run rule.
-    apply_filter();
+    // finish: suffix filter (when it was not applied up front), remaining lower-bound LCP marks, N-run rule
+    if (!prefilter) apply_filter();
     int t4 = timer.mark();
     if (doubling_rounds && s) {
         lcp_complete_kernel<<<grid_for(s, 1), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get());
@@ -603,6 +631,18 @@ void Build::run(SufrB200Result* out) {
     }
     int t5 = timer.mark();
     n_run_rule();
+    if (sliced) {
+        if (shard_offset + shard_count > s) throw Error(SUFR_B200_ERR_INTERNAL, "shard slice out of range");
+        auto sa2 = dalloc<uint32_t>(shard_count);
+        auto lcp2 = dalloc<uint32_t>(shard_count);
+        if (shard_count) {
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(sa2.get(), d_sa.get() + shard_offset, shard_count * 4, cudaMemcpyDeviceToDevice, st()));
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(lcp2.get(), d_lcp.get() + shard_offset, shard_count * 4, cudaMemcpyDeviceToDevice, st()));
+        }
+        d_sa = std::move(sa2);
+        d_lcp = std::move(lcp2);
+        s = shard_count;
+    }
 
     // shard bookkeeping
     if (args.world_size <= 1) total_suffixes = s;

@@ -94,19 +94,27 @@ __global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, 
     }
 }
 
-// Shard selection (multi-GPU): only suffixes whose first key word lies in [lo, hi) belong to this rank.
-struct ShardIn {
+__device__ __forceinline__ bool indexed_byte(uint8_t c) { return c == '$' || c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// Selection of the suffixes this build sorts: the suffix filter (sufr_builder.rs:446-449) applied up front,
+// and / or the key range [lo, hi) of this rank's shard (multi-GPU).  Order-preserving compaction.
+struct SelectIn {
     KeySpec ks;
     uint64_t n;
     int descending;
+    int use_range;
     uint64_t lo, hi;  // hi == 0 means "no upper bound"
+    const uint8_t* text;
+    int filter;
     __device__ uint32_t operator()(uint64_t e) const {
         uint64_t p = descending ? n - 1 - e : e;
+        if (filter && !indexed_byte(text[p])) return 0u;
+        if (!use_range) return 1u;
         uint64_t k = key_word(ks, p, 0);
         return (k >= lo && (hi == 0 || k < hi)) ? 1u : 0u;
     }
 };
-struct ShardOut {
+struct SelectOut {
     KeySpec ks;
     uint64_t n;
     int descending;
@@ -121,7 +129,6 @@ struct ShardOut {
     }
 };
 
-__device__ __forceinline__ bool indexed_byte(uint8_t c) { return c == '$' || c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
 // Histogram of the top `hbits` bits of the first key word over the indexed suffixes (splitter selection).
 __global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n, uint32_t hbits,

@@ -284,3 +284,26 @@ def test_config1_10mbp_random_dna(S, n):
     assert np.array_equal(got.sa, want.sa)
     assert np.array_equal(got.lcp, want.lcp)
     got.free()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_deep_repeats_fall_back_to_full_sort(S, world):
+    """A shard cannot run prefix doubling on its own (it needs the rank of every position): the build is
+    redone unsharded on each rank and the rank's slice is cut out.  Result still concatenates exactly."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = random.Random(world)
+    text = rand_text(rng, 3000, b"ACGTN")[:-1] + b"ACGGT" * 1500 + rand_text(rng, 3000, b"ACGT")[:-1] + b"GT" * 2000 + b"$"
+    for kw in (dict(is_dna=True), dict(is_dna=True, allow_ambiguity=True)):
+        want = O.oracle_build(text, num_partitions=16, threads=4, **kw)
+        shards = [S.build(S.SufrBuilderArgs(text=text, **kw), rank=r, world_size=world) for r in range(world)]
+        assert any(s.c.doubling_rounds > 0 for s in shards)
+        meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+        offs, total = shard_layout(meta)
+        assert total == want.num_suffixes
+        for r, s in enumerate(shards):
+            assert s.total_suffixes == total and s.shard_offset == offs[r]
+            prev = previous_last_suffix(meta, r)
+            if prev is not None and s.num_suffixes:
+                s.patch_seam(prev)
+        assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
+        assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
