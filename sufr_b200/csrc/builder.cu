@@ -12,6 +12,7 @@
 //
 // The oracle (oracle/) is never linked or called from here.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -317,30 +318,54 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
 
     DevBuf<uint64_t> keys_a, keys_b;
     DevBuf<uint32_t> pos_a, pos_b;
-    if (sharded || prefilter) {
+    const int used_bits = (int)(ks.pt.K * ks.pt.bits);
+    uint64_t kept = n;     // suffixes that survive the filter (all ranks' ranges together)
+    uint64_t sort_n = n;   // elements handed to the sort
+    if (prefilter && n) {
+        auto d_cnt = dalloc<unsigned long long>(1);
+        SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
+        count_indexed_kernel<<<grid_for(n, 64), kBlock, 0, st()>>>(d_text.get(), n, d_cnt.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        unsigned long long c = 0;
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&c, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        kept = c;
+    }
+    // Few filtered suffixes (the common case: delimiters, sparse N): no compaction at all, they get the
+    // key ~0 and drop off the end of the sorted array.  Needs an unused low bit in the packed word.
+    const bool sentinel = prefilter && !sharded && used_bits < 64 && (n - kept) * 16 <= n;
+    if (sharded || (prefilter && !sentinel)) {
         SelectIn in{ks, n, descending, sharded ? 1 : 0, lo, hi, d_text.get(), prefilter ? 1 : 0};
-        s = scan_total(n, in, scan::SumU32{}, CountOnly{});
+        s = sharded ? shard_count : kept;  // both exact: histogram of indexed suffixes / indexed count
         keys_a = dalloc<uint64_t>(s);
         pos_a = dalloc<uint32_t>(s);
-        if (s) scan_total(n, in, scan::SumU32{}, SelectOut{ks, n, descending, keys_a.get(), pos_a.get()});
+        if (n) {
+            uint32_t got = scan_total(n, in, scan::SumU32{}, SelectOut{ks, n, descending, keys_a.get(), pos_a.get()});
+            if (got != s) throw Error(SUFR_B200_ERR_INTERNAL, "selection count mismatch");
+        }
+        sort_n = s;
     } else {
-        s = n;
-        keys_a = dalloc<uint64_t>(s);
-        pos_a = dalloc<uint32_t>(s);
-        if (s) {
-            keygen_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(ks, n, descending, keys_a.get(), pos_a.get());
+        s = sentinel ? kept : n;
+        sort_n = n;
+        keys_a = dalloc<uint64_t>(n);
+        pos_a = dalloc<uint32_t>(n);
+        if (n) {
+            keygen_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, descending, d_text.get(), sentinel ? 1 : 0,
+                                                              keys_a.get(), pos_a.get());
             SUFR_KERNEL_CHECK();
             launched();
         }
     }
     t_keys_mark = timer.mark();
-    keys_b = dalloc<uint64_t>(s);
-    pos_b = dalloc<uint32_t>(s);
+    keys_b = dalloc<uint64_t>(sort_n);
+    pos_b = dalloc<uint32_t>(sort_n);
     d_counts = dalloc<uint32_t>(rsort::counts_words());
-    const int used = (int)(ks.pt.K * ks.pt.bits);
-    bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), s, 64 - used,
-                                                      64, d_counts.get(), st(), &ctx.launches, &downsweep_events);
-    sorted_elements = s;
+    // sentinel keys have the unused low bits set, so those bits join the sort in that case
+    bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), sort_n,
+                                                      sentinel ? 0 : 64 - used_bits, 64, d_counts.get(), st(),
+                                                      &ctx.launches, &downsweep_events);
+    sorted_elements = sort_n;
     if (in_b) {
         keys_sorted = std::move(keys_b);
         d_sa = std::move(pos_b);
@@ -369,28 +394,63 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     d_lcp = dalloc<uint32_t>(s);
     if (s == 0) return;
 
-    // round 0: boundaries of the initial sort
+    // round 0: boundaries of the initial sort, fused with the collection of the unresolved elements
     uint32_t word = 0;
     int final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
     ViewAll v0{keys_sorted.get(), d_sa.get()};
-    resolve_kernel<ViewAll><<<grid_for(s, 4), kBlock, 0, st()>>>(v0, s, ks, word, final_word, 1, d_lcp.get());
-    SUFR_KERNEL_CHECK();
-    launched();
-    if (final_word) {
-        keys_sorted.reset();
-        return;
+    uint64_t m = 0, nseg = 0;
+    DevBuf<uint32_t> slot, pos, seg;
+    {
+        uint64_t capacity = final_word ? 1 : std::max<uint64_t>(1u << 20, s / 8);
+        if (const char* dbg = getenv("SUFR_B200_DEBUG_SPARSE_CAP")) capacity = std::max<uint64_t>(1, strtoull(dbg, nullptr, 10));
+        auto act_slot = dalloc<uint32_t>(capacity);
+        auto act_pos = dalloc<uint32_t>(capacity);
+        auto d_cnt = dalloc<unsigned long long>(1);
+        SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
+        resolve0_append_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), s, ks, final_word,
+                                                                   d_lcp.get(), act_slot.get(), act_pos.get(),
+                                                                   d_cnt.get(), capacity);
+        SUFR_KERNEL_CHECK();
+        launched();
+        if (final_word) {
+            keys_sorted.reset();
+            return;
+        }
+        unsigned long long cnt = 0;
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&cnt, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        if (cnt == 0) {
+            keys_sorted.reset();
+            return;
+        }
+        if (cnt <= capacity) {
+            // sparse: order the list by SA slot, then number the segments
+            m = cnt;
+            auto slot_b = dalloc<uint32_t>(m);
+            auto pos_b = dalloc<uint32_t>(m);
+            bool in_b = rsort::sort_pairs<uint32_t, uint32_t>(act_slot.get(), slot_b.get(), act_pos.get(), pos_b.get(), m, 0,
+                                                              bits_for(s - 1), d_counts.get(), st(), &ctx.launches);
+            if (in_b) { std::swap(act_slot, slot_b); std::swap(act_pos, pos_b); }
+            slot = std::move(act_slot);
+            pos = std::move(act_pos);
+            seg = dalloc<uint32_t>(m);
+            nseg = scan_total(m, SparseSegIn{keys_sorted.get(), slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
+        } else {
+            // dense (repetitive text): order-preserving compaction by scan
+            act_slot.reset();
+            act_pos.reset();
+            unsigned long long tot = scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{}, CountOnlyU64{});
+            m = (uint32_t)tot;
+            nseg = tot >> 32;
+            slot = dalloc<uint32_t>(m);
+            pos = dalloc<uint32_t>(m);
+            seg = dalloc<uint32_t>(m);
+            scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{},
+                       ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()});
+        }
     }
-    unsigned long long tot = scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{}, CountOnlyU64{});
-    uint64_t m = (uint32_t)tot, nseg = tot >> 32;
-    if (m == 0) {
-        keys_sorted.reset();
-        return;
-    }
-    auto slot = dalloc<uint32_t>(m);
-    auto pos = dalloc<uint32_t>(m);
-    auto seg = dalloc<uint32_t>(m);
-    scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{}, ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()});
     keys_sorted.reset();
+    unsigned long long tot = 0;
 
     // Full sort: after kMaxWordRounds words switch to prefix doubling (depth doubles per round).
     const uint32_t kMaxWordRounds = 3;

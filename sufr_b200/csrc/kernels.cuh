@@ -82,19 +82,51 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(const uint8_t* __restrict_
 }
 
 // ------------------------------------------------------------------ first key word of every suffix
+__device__ __forceinline__ bool indexed_byte(uint8_t c) { return c == '$' || c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
 // Element e of the sort input is suffix e (full sort) or n-1-e (mask / max-query-len: the stable sort
 // then leaves equal keys in position-descending order, the reference's tie rule, sufr_builder.rs:701-703).
+// With `filter`, suffixes the reference does not index (sufr_builder.rs:446-449) get the key ~0, which no
+// real key equals when the packed word has unused low bits: they sort behind everything and are dropped.
 __global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, int descending,
+                                                        const uint8_t* __restrict__ text, int filter,
                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         uint64_t p = descending ? n - 1 - e : e;
-        keys[e] = key_word(ks, p, 0);
+        keys[e] = (filter && !indexed_byte(text[p])) ? ~0ull : key_word(ks, p, 0);
         pos[e] = (uint32_t)p;
     }
 }
 
-__device__ __forceinline__ bool indexed_byte(uint8_t c) { return c == '$' || c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+// Number of indexed suffixes (16 bytes per load).
+__global__ void __launch_bounds__(kBlock) count_indexed_kernel(const uint8_t* __restrict__ text, uint64_t n,
+                                                               unsigned long long* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nvec = (((uintptr_t)text) & 15) == 0 ? n / 16 : 0;
+    unsigned long long c = 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        uint4 x = reinterpret_cast<const uint4*>(text)[v];
+        uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) c += indexed_byte((uint8_t)(w[k] >> (8 * b))) ? 1 : 0;
+    }
+    for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        c += indexed_byte(text[i]) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+    __shared__ unsigned long long part[kBlock / 32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kBlock / 32; w++) t += part[w];
+        if (t) atomicAdd(out, t);
+    }
+}
+
 
 // Selection of the suffixes this build sorts: the suffix filter (sufr_builder.rs:446-449) applied up front,
 // and / or the key range [lo, hi) of this rank's shard (multi-GPU).  Order-preserving compaction.
@@ -191,6 +223,75 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(View v, uint64_t m, Key
         }
     }
 }
+
+// Round 0 in one pass over the sorted keys: LCP of every boundary (as resolve_kernel) and, because the
+// unresolved elements are normally a tiny fraction, an UNORDERED warp-aggregated append of (slot, position)
+// of every element that is still in a group of size > 1.  The short list is then sorted by slot.
+__global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t* __restrict__ keys,
+                                                                 const uint32_t* __restrict__ pos, uint64_t s,
+                                                                 KeySpec ks, int final_word,
+                                                                 uint32_t* __restrict__ lcp,
+                                                                 uint32_t* __restrict__ act_slot,
+                                                                 uint32_t* __restrict__ act_pos,
+                                                                 unsigned long long* __restrict__ act_count,
+                                                                 uint64_t capacity) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < s; j0 += stride) {
+        const uint64_t j = j0 + lane;
+        bool active = false;
+        uint32_t p = 0;
+        if (j < s) {
+            uint64_t kj = keys[j];
+            p = pos[j];
+            bool head = true;
+            if (j == 0) {
+                lcp[0] = 0;
+            } else {
+                uint64_t kp = keys[j - 1];
+                head = kp != kj;
+                if (head) {
+                    lcp[j] = lcp_from_words(ks, kp, kj, 0, pos[j - 1], p);
+                } else if (final_word) {
+                    uint64_t la = key_len(ks, pos[j - 1]), lb = key_len(ks, p);
+                    lcp[j] = (uint32_t)(la < lb ? la : lb);
+                } else {
+                    lcp[j] = kLcpPending;
+                }
+            }
+            if (!final_word) active = !head || (j + 1 < s && keys[j + 1] == kj);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, active);
+        if (m) {
+            int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(act_count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (active) {
+                unsigned long long idx = base + __popc(m & lt_mask);
+                if (idx < capacity) {
+                    act_slot[idx] = (uint32_t)j;
+                    act_pos[idx] = p;
+                }
+            }
+        }
+    }
+}
+// segment ids of the slot-sorted active list: a new segment starts where the key differs from the
+// previous SA slot's key
+struct SparseSegIn {
+    const uint64_t* keys;
+    const uint32_t* slot;
+    __device__ uint32_t operator()(uint64_t a) const {
+        uint32_t j = slot[a];
+        return (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+    }
+};
+struct SparseSegOut {
+    uint32_t* seg;
+    __device__ void operator()(uint64_t a, uint32_t, uint32_t incl) const { seg[a] = incl - 1; }
+};
 
 // Compaction of the elements that are still in a group of size > 1.  Sum-scan input: bit 0 = active,
 // bit 32 = active and first of its group.

@@ -148,7 +148,14 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
             unsigned vm = __ballot_sync(0xffffffffu, valid);
             uint32_t r = 0;
             if (valid) {
-                unsigned peers = __match_any_sync(vm, d);
+                // lanes holding the same digit, by one vote per digit bit (match.any saturates the ADU pipe:
+                // profiles/r1_v0_downsweep_match_any_raw.csv)
+                unsigned peers = vm;
+#pragma unroll
+                for (int b = 0; b < RADIX_BITS; b++) {
+                    unsigned vote = __ballot_sync(vm, (d >> b) & 1u);
+                    peers &= ((d >> b) & 1u) ? vote : ~vote;
+                }
                 int leader = __ffs(peers) - 1;
                 uint32_t old = 0;
                 if (lane == leader) {

@@ -307,3 +307,15 @@ def test_sharded_deep_repeats_fall_back_to_full_sort(S, world):
                 s.patch_seam(prev)
         assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
         assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
+
+
+def test_dense_active_set_uses_scan_compaction(S, monkeypatch):
+    """Repetitive texts overflow the sparse append buffer of round 0; the ordered scan compaction takes over.
+    (Forced here with a tiny buffer; the library reads the knob per build.)"""
+    monkeypatch.setenv("SUFR_B200_DEBUG_SPARSE_CAP", "7")
+    rng = random.Random(5)
+    text = rand_text(rng, 40000, b"ACGT", repeat_p=0.2, max_rep=300)
+    gpu_vs_oracle(S, text, is_dna=True)
+    gpu_vs_oracle(S, text, seed_mask="111010010100110111")
+    monkeypatch.delenv("SUFR_B200_DEBUG_SPARSE_CAP")
+    gpu_vs_oracle(S, text, is_dna=True)
