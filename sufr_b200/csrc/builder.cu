@@ -157,6 +157,7 @@ class Build {
     DevBuf<uint64_t> d_nstarts, d_nends;
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
+    DevBuf<uint32_t> d_isa;     // inverse suffix array (only when prefix doubling ran)
     DevBuf<uint32_t> d_counts;  // radix sort count matrix
     uint64_t shard_offset = 0, shard_count = 0, total_suffixes = 0;
     bool full_set_ = true;  // every text position is being sorted on this rank (prefix doubling needs that)
@@ -511,16 +512,17 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
 void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
                      uint64_t h) {
     if (!full_set_) throw NeedFullSort{};
-    auto isa = dalloc<uint32_t>(n);
-    isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa.get());
+    d_isa = dalloc<uint32_t>(n);
+    uint32_t* const isa_ptr = d_isa.get();
+    isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa_ptr);
     SUFR_KERNEL_CHECK();
     launched();
-    scan_total(m, GroupStartIn{seg.get()}, scan::MaxU32{}, GroupRankOut{slot.get(), pos.get(), isa.get()});
+    scan_total(m, GroupStartIn{seg.get()}, scan::MaxU32{}, GroupRankOut{slot.get(), pos.get(), isa_ptr});
     while (m > 0) {
         if (doubling_rounds > 64) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling did not converge");
         doubling_rounds++;
         auto ck = dalloc<uint64_t>(m);
-        doubling_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, n, h, pos.get(), seg.get(), isa.get(), ck.get());
+        doubling_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, n, h, pos.get(), seg.get(), isa_ptr, ck.get());
         SUFR_KERNEL_CHECK();
         launched();
         segmented_sort_u64key(ck, pos, m, 32 + (nseg > 1 ? bits_for(nseg - 1) : 0));
@@ -529,7 +531,7 @@ void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint3
         launched();
         uint32_t mark = kLcpLowerBound | (uint32_t)(h < 0x7FFFFFFFull ? h : 0x7FFFFFFFull);
         scan_total(m, DoublingStartIn{ck.get()}, scan::MaxU32{},
-                   DoublingRankOut{ck.get(), slot.get(), pos.get(), isa.get(), d_lcp.get(), mark});
+                   DoublingRankOut{ck.get(), slot.get(), pos.get(), isa_ptr, d_lcp.get(), mark});
         unsigned long long tot = scan_total(m, DoublingActiveIn{ck.get(), m}, scan::SumU64{}, CountOnlyU64{});
         uint64_t m2 = (uint32_t)tot, nseg2 = tot >> 32;
         if (m2 == 0) break;
@@ -669,6 +671,7 @@ void Build::run(SufrB200Result* out) {
         SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
         d_sa.reset();
         d_lcp.reset();
+        d_isa.reset();
         refine_rounds = doubling_rounds = 0;
         for (auto& ev : downsweep_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
         downsweep_events.clear();
@@ -681,14 +684,18 @@ void Build::run(SufrB200Result* out) {
     int t2 = t_sorted_mark;
     int t3 = timer.mark();
 
-    // finish: suffix filter (when it was not applied up front), remaining lower-bound LCP marks, N-run rule
-    if (!prefilter) apply_filter();
-    int t4 = timer.mark();
+    // finish: lower-bound LCP marks left by prefix doubling (text order, on the unfiltered arrays), then the
+    // suffix filter when it was not applied up front, then the N-run rule
     if (doubling_rounds && s) {
-        lcp_complete_kernel<<<grid_for(s, 1), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get());
+        if (!d_isa || s != n) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling ran on a partial suffix set");
+        uint64_t chunks = div_up(n, kPlcpChunk);
+        plcp_complete_kernel<<<grid_for(chunks, 1), kBlock, 0, st()>>>(ks, n, d_sa.get(), d_isa.get(), d_lcp.get());
         SUFR_KERNEL_CHECK();
         launched();
     }
+    d_isa.reset();
+    int t4 = timer.mark();
+    if (!prefilter) apply_filter();
     int t5 = timer.mark();
     n_run_rule();
     if (sliced) {
@@ -744,8 +751,8 @@ void Build::run(SufrB200Result* out) {
     tm.keys_ms = timer.ms(t1, t_keys_mark);
     tm.sort_ms = timer.ms(t_keys_mark, t2);
     tm.refine_ms = timer.ms(t2, t3);
-    tm.finish_ms = timer.ms(t3, t4) + timer.ms(t5, t6);
-    tm.lcp_ms = timer.ms(t4, t5);
+    tm.finish_ms = timer.ms(t4, t6);
+    tm.lcp_ms = timer.ms(t3, t4);
     tm.total_ms = timer.ms(t0, t6);
     for (auto& ev : downsweep_events) {
         float t = 0;

@@ -436,24 +436,46 @@ struct DoublingActiveOut {
 };
 
 // ------------------------------------------------------------------ LCP completion
-// Entries marked kLcpLowerBound|h are computed by direct word-wise comparison from offset h.
+// Boundaries created by prefix doubling only carry a lower bound (kLcpLowerBound | h).  They are
+// completed in TEXT order, Kasai / PLCP style: with phi(i) = the suffix preceding suffix i in the
+// suffix array, lcp(i, phi(i)) >= lcp(i-1, phi(i-1)) - 1, so a thread that walks a chunk of consecutive
+// text positions extends each match from where the previous one ended instead of from the lower
+// bound.  Total work is O(n + chunks * LCP) instead of O(sum of LCP^2) for tandem repeats.
+// Needs the inverse suffix array of ALL positions (available whenever doubling ran).
 // Pairs that both start inside recorded N runs use the reference's shortcut (sufr_builder.rs:305-307).
-__global__ void __launch_bounds__(kBlock) lcp_complete_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
-                                                              uint32_t* __restrict__ lcp) {
+constexpr uint32_t kPlcpChunk = 512;
+
+__global__ void __launch_bounds__(kBlock) plcp_complete_kernel(KeySpec ks, uint64_t n, const uint32_t* __restrict__ sa,
+                                                               const uint32_t* __restrict__ isa,
+                                                               uint32_t* __restrict__ lcp) {
+    const uint64_t chunks = (n + kPlcpChunk - 1) / kPlcpChunk;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
-        uint32_t v = lcp[j];
-        if (v == kLcpPending || !(v & kLcpLowerBound) || j == 0) continue;
-        uint64_t pa = sa[j - 1], pb = sa[j];
-        uint64_t ea, eb;
-        if (ks.num_n_ranges && n_run_end(ks, pa, ea) && n_run_end(ks, pb, eb)) {
-            uint64_t ra = ea - pa, rb = eb - pb;
-            lcp[j] = (uint32_t)(ra < rb ? ra : rb);
-            continue;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += stride) {
+        uint64_t i0 = c * kPlcpChunk;
+        uint64_t i1 = i0 + kPlcpChunk < n ? i0 + kPlcpChunk : n;
+        uint64_t l = 0;  // lcp(i-1, phi(i-1)), a lower bound + 1 for position i
+        for (uint64_t i = i0; i < i1; i++) {
+            uint32_t j = isa[i];
+            uint32_t v = lcp[j];
+            if (v == kLcpPending || !(v & kLcpLowerBound) || j == 0) {
+                l = (v == kLcpPending) ? 0 : v;  // exact value known from the key words
+                continue;
+            }
+            uint64_t prev = sa[j - 1];
+            uint64_t ea, eb;
+            if (ks.num_n_ranges && n_run_end(ks, prev, ea) && n_run_end(ks, i, eb)) {
+                uint64_t ra = ea - prev, rb = eb - i;
+                l = ra < rb ? ra : rb;  // <= the true LCP, so still a valid bound for the next position
+                lcp[j] = (uint32_t)l;
+                continue;
+            }
+            uint64_t lower = v & ~kLcpLowerBound;
+            if (l > 0 && l - 1 > lower) lower = l - 1;
+            l = lcp_direct(ks, prev, i, lower);
+            uint64_t out = l;
+            if (ks.mode == kModeMaxQueryLen && out > ks.cap) out = ks.cap;
+            lcp[j] = (uint32_t)out;
         }
-        uint64_t l = lcp_direct(ks, pa, pb, v & ~kLcpLowerBound);
-        if (ks.mode == kModeMaxQueryLen && l > ks.cap) l = ks.cap;
-        lcp[j] = (uint32_t)l;
     }
 }
 

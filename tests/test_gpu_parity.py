@@ -319,3 +319,37 @@ def test_dense_active_set_uses_scan_compaction(S, monkeypatch):
     gpu_vs_oracle(S, text, seed_mask="111010010100110111")
     monkeypatch.delenv("SUFR_B200_DEBUG_SPARSE_CAP")
     gpu_vs_oracle(S, text, is_dna=True)
+
+
+@pytest.mark.parametrize("name,size,kw", [
+    ("config2b", 400_000, {}),
+    ("config3", 300_000, dict(record_len=10_000)),
+    ("config4", 500_000, {}),
+    ("config5", 300_000, dict(max_unit=40, max_copies=300)),
+])
+def test_baseline_configs_small_vs_oracle(S, name, size, kw):
+    """The BASELINE.json configs 2b-5 (generators: workloads.py) at sizes the oracle sorts in seconds."""
+    import workloads
+    w = workloads.ALL[name](size, **kw)
+    flags = dict(w.flags)
+    want = O.oracle_build(w.text, threads=8, sequence_starts=w.sequence_starts, sequence_names=w.sequence_names,
+                          index_bits=w.index_bits, **flags)
+    got = S.build(S.SufrBuilderArgs(text=w.text, sequence_starts=w.sequence_starts,
+                                    sequence_names=w.sequence_names, **flags), index_bits=w.index_bits)
+    assert got.text == want.text
+    assert got.n_ranges == want.n_ranges
+    if name == "config3":
+        assert int(want.lcp.max()) < 32  # precondition: no two suffixes share Q residues
+    assert np.array_equal(got.sa, want.sa)
+    assert np.array_equal(got.lcp, want.lcp)
+    # the size-independent checks used at full size agree with the oracle comparison
+    sys_path_tools = str(__import__("conftest").ROOT / "tools")
+    import sys
+    sys.path.insert(0, sys_path_tools)
+    from verify import check_pairs, check_positions
+    ranks = np.random.default_rng(0).integers(0, got.num_suffixes, 500)
+    assert check_pairs(got.text, got.sa, got.lcp, ranks, seed_mask=flags.get("seed_mask"),
+                       max_query_len=flags.get("max_query_len"), n_ranges=got.n_ranges) == []
+    assert check_positions(got.text, got.sa, is_dna=flags.get("is_dna", False),
+                           allow_ambiguity=flags.get("allow_ambiguity", False))
+    got.free()
