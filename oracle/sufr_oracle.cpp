@@ -133,6 +133,7 @@ struct Builder {
     int threads = 1;
     PhaseTimes times;
     std::string error;
+    mutable bool pivot_error = false;
 
     const SeedMask* mptr() const { return has_mask ? &mask : nullptr; }
 
@@ -316,6 +317,19 @@ struct Builder {
         std::vector<T> pivots;
         if (num_partitions <= 1) return pivots;
         size_t num_pivots = num_partitions - 1;
+        if (is_dna) {
+            // The reference draws positions until it has num_pivots distinct ACGT$ ones and loops forever when
+            // the text has fewer (sufr_builder.rs:787-796).  The oracle reports that case instead of hanging.
+            size_t eligible = 0;
+            for (size_t i = 0; i < text_len && eligible < num_pivots; i++) {
+                uint8_t c = text[i];
+                if (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '$') eligible++;
+            }
+            if (eligible < num_pivots) {
+                pivot_error = true;
+                return pivots;
+            }
+        }
         uint64_t state = random_seed > 0 ? random_seed : 0x5DEECE66Dull ^ (uint64_t)text_len;
         std::unordered_set<uint64_t> seen;
         std::vector<uint64_t> order;
@@ -351,6 +365,10 @@ struct Builder {
         double t0 = now_s();
         std::vector<T> pivots = select_pivots(raw_parts, random_seed);
         times.pivots_s = now_s() - t0;
+        if (pivot_error) {
+            error = "reference would loop forever: fewer ACGT$ positions than pivots (sufr_builder.rs:787-796)";
+            return false;
+        }
 
         // HOT LOOP A (sufr_builder.rs:442-462): every indexed position -> upper_bound -> partition
         t0 = now_s();

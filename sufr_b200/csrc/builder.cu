@@ -454,11 +454,17 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     unsigned long long tot = 0;
 
     // Full sort: after kMaxWordRounds words switch to prefix doubling (depth doubles per round).
-    const uint32_t kMaxWordRounds = 3;
+    // When this attempt sorts only a subset of the positions (filter applied up front / one shard), doubling
+    // means redoing the build over all positions, so shallow repeats (few unresolved elements) get more
+    // word rounds first.
+    const uint32_t kMaxWordRounds = 3, kPatientWordRounds = 48;
     while (m > 0) {
         if (ks.mode == kModeFull && word >= kMaxWordRounds) {
-            doubling(slot, pos, seg, m, nseg, (uint64_t)(word + 1) * K);
-            return;
+            bool patient = !full_set_ && word < kPatientWordRounds && m * 16 < s;
+            if (!patient) {
+                doubling(slot, pos, seg, m, nseg, (uint64_t)(word + 1) * K);
+                return;
+            }
         }
         word++;
         refine_rounds++;

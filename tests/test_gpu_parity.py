@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden files.
 Bit-exact: SA, LCP, transformed text, and the whole `.sufr` file."""
 import random
+import zlib
 
 import numpy as np
 import pytest
@@ -18,9 +19,16 @@ def S():
     return sufr_b200
 
 
+def seed_of(*parts) -> int:
+    """Deterministic seed (Python's hash() of str is randomised per process)."""
+    return zlib.crc32(repr(parts).encode())
+
+
 def gpu_vs_oracle(S, text, index_bits=32, **kw):
-    want = O.oracle_build(text, num_partitions=kw.pop("oracle_partitions", 16), threads=4,
-                          index_bits=index_bits, **kw)
+    # few partitions on tiny texts: the reference (and so the oracle) cannot draw more distinct ACGT$ pivots
+    # than the text has (it would loop forever, sufr_builder.rs:787-796)
+    parts = kw.pop("oracle_partitions", 16 if len(text) > 2000 else 1)
+    want = O.oracle_build(text, num_partitions=parts, threads=4, index_bits=index_bits, **kw)
     got = S.build(S.SufrBuilderArgs(text=text, **kw), index_bits=index_bits)
     try:
         assert got.text == want.text
@@ -115,7 +123,7 @@ ALPHABETS = {
 @pytest.mark.parametrize("n", [1, 2, 5, 63, 64, 65, 1000, 30000])
 def test_full_sort_random(S, name, n):
     alphabet, flags = ALPHABETS[name]
-    rng = random.Random(hash((name, n)) & 0xFFFFFF)
+    rng = random.Random(seed_of(name, n))
     text = rand_text(rng, n, alphabet, repeat_p=0.05)
     if n <= 2:
         text = text[:-1] + b"$$$"[: 4 - n]  # the reference needs text_len >= 4 (partition count n/4)
@@ -127,7 +135,7 @@ def test_full_sort_random(S, name, n):
 @pytest.mark.parametrize("name", ["acgt", "dna_amb", "protein", "binary"])
 def test_seed_mask_random(S, mask, name):
     alphabet, flags = ALPHABETS[name]
-    rng = random.Random(hash((mask, name)) & 0xFFFFFF)
+    rng = random.Random(seed_of(mask, name))
     text = rand_text(rng, rng.randrange(50, 20000), alphabet, repeat_p=0.05)
     gpu_vs_oracle(S, text, seed_mask=mask, **flags)
 

