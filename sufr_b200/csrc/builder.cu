@@ -154,6 +154,10 @@ class Build {
     DevBuf<uint8_t> d_text;     // transformed text
     DevBuf<uint64_t> d_words;   // packed text
     DevBuf<uint32_t> d_maskpos;
+    DevBuf<uint64_t> d_packed2, d_irr;  // 2-bit fast path (keys.cuh: first_key_fast2)
+    DevBuf<uint8_t> d_cls;
+    bool sentinel_ = false;             // filtered suffixes ride through the sort with key ~0
+    uint64_t sort_n_ = 0;               // elements handed to the main sort (>= s when sentinel_)
     DevBuf<uint64_t> d_nstarts, d_nends;
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
@@ -202,15 +206,19 @@ static int bits_for(uint64_t v) {  // number of bits needed to represent values 
 void Build::encode(const uint8_t* d_raw) {
     d_text = dalloc<uint8_t>(n + 16);
     auto d_present = dalloc<uint32_t>(256);
+    auto d_sample = dalloc<unsigned long long>(256);
     SUFR_CUDA_CHECK(cudaMemsetAsync(d_present.get(), 0, 256 * sizeof(uint32_t), st()));
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_sample.get(), 0, 256 * sizeof(unsigned long long), st()));
     if (n) {
         transform_kernel<<<grid_for(n, 16), kBlock, 0, st()>>>(d_raw, d_text.get(), n, args.ignore_softmask,
-                                                               d_present.get());
+                                                               d_present.get(), d_sample.get());
         SUFR_KERNEL_CHECK();
         launched();
     }
     uint32_t present[256];
+    unsigned long long sample[256];
     SUFR_CUDA_CHECK(cudaMemcpyAsync(present, d_present.get(), sizeof(present), cudaMemcpyDeviceToHost, st()));
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(sample, d_sample.get(), sizeof(sample), cudaMemcpyDeviceToHost, st()));
     SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
     uint8_t lut[256];
     alphabet = 0;
@@ -235,6 +243,52 @@ void Build::encode(const uint8_t* d_raw) {
         launched();
     }
     pt.words = d_words.get();
+    ks.text = d_text.get();
+
+    // 2-bit fast path for the first sort: full sort of a text dominated by four byte values (DNA).  The four
+    // most frequent bytes of a 1/64 sample are the "regular" symbols; any choice is correct, it only decides
+    // how many keys contain fill.
+    ks.fast2 = 0;
+    if (ks.mode == kModeFull && n >= 4096 && !getenv("SUFR_B200_DEBUG_NO_FAST2")) {
+        int order[256];
+        for (int b = 0; b < 256; b++) order[b] = b;
+        std::sort(order, order + 256, [&](int a, int b) { return sample[a] != sample[b] ? sample[a] > sample[b] : a < b; });
+        unsigned long long total = 0, top4 = 0;
+        for (int b = 0; b < 256; b++) total += sample[b];
+        for (int k = 0; k < 4; k++) top4 += sample[order[k]];
+        if (total > 0 && sample[order[3]] > 0 && top4 * 16 >= total * 15) {
+            int reg[4] = {order[0], order[1], order[2], order[3]};
+            std::sort(reg, reg + 4);
+            uint8_t cls[256], cls2[256];
+            for (int b = 0; b < 256; b++) {
+                int c = 0, rank = -1;
+                for (int k = 0; k < 4; k++) {
+                    if (reg[k] < b) c++;
+                    if (reg[k] == b) rank = k;
+                }
+                cls[b] = (uint8_t)(rank >= 0 ? rank : c);
+                cls2[b] = (uint8_t)(rank >= 0 ? rank : ((c > 3 ? 3 : c) | 4));
+            }
+            uint64_t words2 = (div_up(n, 32) + 3) & ~1ull;  // even, with padding words generated by the kernel
+            d_packed2 = dalloc<uint64_t>(words2 + 2);
+            d_irr = dalloc<uint64_t>(words2 / 2 + 2);
+            d_cls = dalloc<uint8_t>(256);
+            auto d_cls2 = dalloc<uint8_t>(256);
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(d_cls.get(), cls, 256, cudaMemcpyHostToDevice, st()));
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(d_cls2.get(), cls2, 256, cudaMemcpyHostToDevice, st()));
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_packed2.get() + words2, 0, 2 * 8, st()));
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_irr.get() + words2 / 2, 0xFF, 2 * 8, st()));
+            pack2_kernel<<<grid_for(words2), kBlock, 0, st()>>>(d_text.get(), n, d_cls2.get(), words2, d_packed2.get(),
+                                                               reinterpret_cast<uint32_t*>(d_irr.get()));
+            SUFR_KERNEL_CHECK();
+            launched();
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            ks.fast2 = 1;
+            ks.packed2 = d_packed2.get();
+            ks.irr = d_irr.get();
+            ks.cls = d_cls.get();
+        }
+    }
     SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));  // lut / present are freed on return
 }
 
@@ -336,6 +390,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     // Few filtered suffixes (the common case: delimiters, sparse N): no compaction at all, they get the
     // key ~0 and drop off the end of the sorted array.  Needs an unused low bit in the packed word.
     const bool sentinel = prefilter && !sharded && used_bits < 64 && (n - kept) * 16 <= n;
+    sentinel_ = sentinel;
     if (sharded || (prefilter && !sentinel)) {
         SelectIn in{ks, n, descending, sharded ? 1 : 0, lo, hi, d_text.get(), prefilter ? 1 : 0};
         s = sharded ? shard_count : kept;  // both exact: histogram of indexed suffixes / indexed count
@@ -362,11 +417,14 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     keys_b = dalloc<uint64_t>(sort_n);
     pos_b = dalloc<uint32_t>(sort_n);
     d_counts = dalloc<uint32_t>(rsort::counts_words());
-    // sentinel keys have the unused low bits set, so those bits join the sort in that case
+    // 3-bit keys: all used bits (sentinel keys have the unused low bits set, so those join the sort then).
+    // 2-bit fast path: only the top kFast2SortBits; ties go to the exact refinement.
+    const int begin_bit = ks.fast2 ? 64 - kFast2SortBits : (sentinel ? 0 : 64 - used_bits);
     bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), sort_n,
-                                                      sentinel ? 0 : 64 - used_bits, 64, d_counts.get(), st(),
-                                                      &ctx.launches, &downsweep_events);
+                                                      begin_bit, 64, d_counts.get(), st(), &ctx.launches,
+                                                      &downsweep_events);
     sorted_elements = sort_n;
+    sort_n_ = sort_n;
     if (in_b) {
         keys_sorted = std::move(keys_b);
         d_sa = std::move(pos_b);
@@ -392,25 +450,38 @@ void Build::segmented_sort_u64key(DevBuf<uint64_t>& ck, DevBuf<uint32_t>& pos, u
 void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     const uint32_t K = ks.pt.K;
     const int used = (int)(K * ks.pt.bits);
-    d_lcp = dalloc<uint32_t>(s);
-    if (s == 0) return;
+    // In fast2 + sentinel mode the filtered suffixes sit inside the last group until the refinement has
+    // pushed them to the very end, so round 0 looks at all sort_n_ elements there.
+    const bool fast2 = ks.fast2 != 0;
+    const uint64_t r0n = (fast2 && sentinel_) ? sort_n_ : s;
+    d_lcp = dalloc<uint32_t>(r0n);
+    if (r0n == 0) return;
 
-    // round 0: boundaries of the initial sort, fused with the collection of the unresolved elements
-    uint32_t word = 0;
-    int final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
-    ViewAll v0{keys_sorted.get(), d_sa.get()};
+    // round 0: boundaries of the initial sort, fused with the collection of the unresolved elements.
+    // `word` is the last key word (3-bit packing) the groups are known to agree on; the fast path has only
+    // sorted a 2-bit approximation of the first symbols, so its refinement starts with word 0.
+    int word = fast2 ? -1 : 0;
+    int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
+    const uint64_t cmp_mask = fast2 ? kFast2CmpMask : ~0ull;
+    ViewAll v0{keys_sorted.get(), d_sa.get(), cmp_mask};
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, pos, seg;
     {
-        uint64_t capacity = final_word ? 1 : std::max<uint64_t>(1u << 20, s / 8);
+        uint64_t capacity = final_word ? 1 : std::max<uint64_t>(1u << 20, r0n / 8);
         if (const char* dbg = getenv("SUFR_B200_DEBUG_SPARSE_CAP")) capacity = std::max<uint64_t>(1, strtoull(dbg, nullptr, 10));
         auto act_slot = dalloc<uint32_t>(capacity);
         auto act_pos = dalloc<uint32_t>(capacity);
         auto d_cnt = dalloc<unsigned long long>(1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
-        resolve0_append_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), s, ks, final_word,
-                                                                   d_lcp.get(), act_slot.get(), act_pos.get(),
-                                                                   d_cnt.get(), capacity);
+        if (fast2) {
+            resolve0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks,
+                                                                        d_lcp.get(), act_slot.get(), act_pos.get(),
+                                                                        d_cnt.get(), capacity);
+        } else {
+            resolve0_append_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks, final_word,
+                                                                         d_lcp.get(), act_slot.get(), act_pos.get(),
+                                                                         d_cnt.get(), capacity);
+        }
         SUFR_KERNEL_CHECK();
         launched();
         if (final_word) {
@@ -430,23 +501,24 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             auto slot_b = dalloc<uint32_t>(m);
             auto pos_b = dalloc<uint32_t>(m);
             bool in_b = rsort::sort_pairs<uint32_t, uint32_t>(act_slot.get(), slot_b.get(), act_pos.get(), pos_b.get(), m, 0,
-                                                              bits_for(s - 1), d_counts.get(), st(), &ctx.launches);
+                                                              bits_for(r0n - 1), d_counts.get(), st(), &ctx.launches);
             if (in_b) { std::swap(act_slot, slot_b); std::swap(act_pos, pos_b); }
             slot = std::move(act_slot);
             pos = std::move(act_pos);
             seg = dalloc<uint32_t>(m);
-            nseg = scan_total(m, SparseSegIn{keys_sorted.get(), slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
+            nseg = scan_total(m, SparseSegIn{keys_sorted.get(), slot.get(), cmp_mask}, scan::SumU32{},
+                              SparseSegOut{seg.get()});
         } else {
             // dense (repetitive text): order-preserving compaction by scan
             act_slot.reset();
             act_pos.reset();
-            unsigned long long tot = scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{}, CountOnlyU64{});
+            unsigned long long tot = scan_total(r0n, ActiveIn<ViewAll>{v0, r0n, 0, sentinel_ ? 1 : 0}, scan::SumU64{}, CountOnlyU64{});
             m = (uint32_t)tot;
             nseg = tot >> 32;
             slot = dalloc<uint32_t>(m);
             pos = dalloc<uint32_t>(m);
             seg = dalloc<uint32_t>(m);
-            scan_total(s, ActiveIn<ViewAll>{v0, s, 0}, scan::SumU64{},
+            scan_total(r0n, ActiveIn<ViewAll>{v0, r0n, 0, sentinel_ ? 1 : 0}, scan::SumU64{},
                        ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()});
         }
     }
@@ -457,7 +529,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // When this attempt sorts only a subset of the positions (filter applied up front / one shard), doubling
     // means redoing the build over all positions, so shallow repeats (few unresolved elements) get more
     // word rounds first.
-    const uint32_t kMaxWordRounds = 3, kPatientWordRounds = 48;
+    const int kMaxWordRounds = 3, kPatientWordRounds = 48;
     while (m > 0) {
         if (ks.mode == kModeFull && word >= kMaxWordRounds) {
             bool patient = !full_set_ && word < kPatientWordRounds && m * 16 < s;
@@ -471,8 +543,8 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
         auto keys = dalloc<uint64_t>(m);
         auto segpos = dalloc<uint64_t>(m);
-        active_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, word, pos.get(), seg.get(), keys.get(),
-                                                               segpos.get());
+        active_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, pos.get(),
+                                                               seg.get(), keys.get(), segpos.get());
         SUFR_KERNEL_CHECK();
         launched();
         {   // stable sort by (segment, key word): LSD, key word first, then the segment bits
@@ -493,17 +565,18 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         launched();
         segpos.reset();
         ViewActive va{keys.get(), pos.get(), seg.get(), slot.get()};
-        resolve_kernel<ViewActive><<<grid_for(m, 2), kBlock, 0, st()>>>(va, m, ks, word, final_word, 0, d_lcp.get());
+        resolve_kernel<ViewActive><<<grid_for(m, 2), kBlock, 0, st()>>>(va, m, ks, (uint32_t)word, final_word, 0,
+                                                                       d_lcp.get());
         SUFR_KERNEL_CHECK();
         launched();
         if (final_word) return;
-        tot = scan_total(m, ActiveIn<ViewActive>{va, m, 0}, scan::SumU64{}, CountOnlyU64{});
+        tot = scan_total(m, ActiveIn<ViewActive>{va, m, 0, sentinel_ ? 1 : 0}, scan::SumU64{}, CountOnlyU64{});
         uint64_t m2 = (uint32_t)tot, nseg2 = tot >> 32;
         if (m2 == 0) return;
         auto slot2 = dalloc<uint32_t>(m2);
         auto pos2 = dalloc<uint32_t>(m2);
         auto seg2 = dalloc<uint32_t>(m2);
-        scan_total(m, ActiveIn<ViewActive>{va, m, 0}, scan::SumU64{},
+        scan_total(m, ActiveIn<ViewActive>{va, m, 0, sentinel_ ? 1 : 0}, scan::SumU64{},
                    ActiveOut<ViewActive>{va, slot2.get(), pos2.get(), seg2.get()});
         slot = std::move(slot2);
         pos = std::move(pos2);

@@ -27,9 +27,12 @@ inline uint32_t grid_for(uint64_t n, int per_thread = 1) {
 // Lowercase ASCII -> 'N' (ignore_softmask) or uppercase; also records which bytes occur.
 __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __restrict__ in,
                                                            uint8_t* __restrict__ out, uint64_t n,
-                                                           int ignore_softmask, uint32_t* __restrict__ present) {
+                                                           int ignore_softmask, uint32_t* __restrict__ present,
+                                                           unsigned long long* __restrict__ sample_counts) {
     __shared__ uint32_t seen[256];
+    __shared__ uint32_t cnt[256];  // byte counts of a 1/64 sample (chooses the 4 "regular" bytes)
     seen[threadIdx.x] = 0;
+    cnt[threadIdx.x] = 0;
     __syncthreads();
     const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const uint64_t nvec = aligned ? n / 16 : 0;
@@ -45,6 +48,7 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
                 uint32_t c = (w[k] >> (8 * b)) & 0xFF;
                 if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
                 seen[c] = 1;
+                if ((v & 63) == 0) atomicAdd(&cnt[c], 1u);
                 r |= c << (8 * b);
             }
             w[k] = r;
@@ -59,6 +63,32 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
     }
     __syncthreads();
     if (seen[threadIdx.x]) present[threadIdx.x] = 1;
+    if (cnt[threadIdx.x]) atomicAdd(&sample_counts[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+}
+
+// 2-bit fast path: one 64-bit word of `packed2` (32 symbols) per thread, and the matching 32 bits of `irr`.
+// cls2[b] = 2-bit code of byte b (rank of a regular byte, min(class, 3) of an irregular one) | 4 if irregular.
+__global__ void __launch_bounds__(kBlock) pack2_kernel(const uint8_t* __restrict__ text, uint64_t n,
+                                                       const uint8_t* __restrict__ cls2, uint64_t num_words,
+                                                       uint64_t* __restrict__ packed2, uint32_t* __restrict__ irr32) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = cls2[threadIdx.x];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < num_words; w += stride) {
+        uint64_t base = w * 32;
+        uint64_t x = 0;
+        uint32_t m = 0;
+        for (uint32_t j = 0; j < 32; j++) {
+            uint64_t i = base + j;
+            uint32_t c = i < n ? lut[text[i]] : 4u;  // beyond the text: irregular, class 0
+            x |= (uint64_t)(c & 3u) << (62 - 2 * j);
+            m |= (c >> 2) << (31 - j);
+        }
+        packed2[w] = x;
+        // irr is addressed as 64-bit words with symbol 0 in the top bit: 32-bit halves are swapped on little-endian
+        irr32[w ^ 1] = m;
+    }
 }
 
 // One 64-bit word (K symbols) per thread.
@@ -94,7 +124,7 @@ __global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, 
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         uint64_t p = descending ? n - 1 - e : e;
-        keys[e] = (filter && !indexed_byte(text[p])) ? ~0ull : key_word(ks, p, 0);
+        keys[e] = (filter && !indexed_byte(text[p])) ? ~0ull : first_key(ks, p);
         pos[e] = (uint32_t)p;
     }
 }
@@ -142,7 +172,7 @@ struct SelectIn {
         uint64_t p = descending ? n - 1 - e : e;
         if (filter && !indexed_byte(text[p])) return 0u;
         if (!use_range) return 1u;
-        uint64_t k = key_word(ks, p, 0);
+        uint64_t k = first_key(ks, p);
         return (k >= lo && (hi == 0 || k < hi)) ? 1u : 0u;
     }
 };
@@ -155,7 +185,7 @@ struct SelectOut {
     __device__ void operator()(uint64_t e, uint32_t v, uint32_t incl) const {
         if (v) {
             uint64_t p = descending ? n - 1 - e : e;
-            keys[incl - 1] = key_word(ks, p, 0);
+            keys[incl - 1] = first_key(ks, p);
             pos[incl - 1] = (uint32_t)p;
         }
     }
@@ -172,7 +202,7 @@ __global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
-        if (!filter || indexed_byte(text[p])) atomicAdd(&sh[(uint32_t)(key_word(ks, p, 0) >> (64 - hbits))], 1u);
+        if (!filter || indexed_byte(text[p])) atomicAdd(&sh[(uint32_t)(first_key(ks, p) >> (64 - hbits))], 1u);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
@@ -184,7 +214,9 @@ __global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n
 struct ViewAll {
     const uint64_t* key;
     const uint32_t* pos;
-    __device__ uint64_t k(uint64_t i) const { return key[i]; }
+    uint64_t cmp_mask;  // ~0, or the sorted top bits of the 2-bit fast path
+    __device__ uint64_t k(uint64_t i) const { return key[i] & cmp_mask; }
+    __device__ uint64_t raw(uint64_t i) const { return key[i]; }
     __device__ uint32_t p(uint64_t i) const { return pos[i]; }
     __device__ bool same_seg(uint64_t i) const { return i > 0; }
     __device__ uint32_t slot(uint64_t i) const { return (uint32_t)i; }
@@ -195,6 +227,7 @@ struct ViewActive {
     const uint32_t* seg;
     const uint32_t* slot_;
     __device__ uint64_t k(uint64_t i) const { return key[i]; }
+    __device__ uint64_t raw(uint64_t i) const { return key[i]; }
     __device__ uint32_t p(uint64_t i) const { return pos[i]; }
     __device__ bool same_seg(uint64_t i) const { return i > 0 && seg[i] == seg[i - 1]; }
     __device__ uint32_t slot(uint64_t i) const { return slot_[i]; }
@@ -278,14 +311,72 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
         }
     }
 }
+// Round 0 of the 2-bit fast path.  Only the top kFast2SortBits of the keys are sorted: a group is a run of
+// equal sorted bits, everything in a group of size > 1 is collected for the exact refinement (which starts
+// at key word 0).  Boundary LCP = clz(x ^ y) / 2 when neither key contains fill, else an exact comparison
+// on the packed text.  Filtered suffixes (key ~0) are inside the last group and never collected... they are
+// collected with it (the refinement sorts them to the very end of the array and then drops them).
+__global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* __restrict__ keys,
+                                                                const uint32_t* __restrict__ pos, uint64_t s,
+                                                                KeySpec ks, uint32_t* __restrict__ lcp,
+                                                                uint32_t* __restrict__ act_slot,
+                                                                uint32_t* __restrict__ act_pos,
+                                                                unsigned long long* __restrict__ act_count,
+                                                                uint64_t capacity) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < s; j0 += stride) {
+        const uint64_t j = j0 + lane;
+        bool active = false;
+        uint32_t p = 0;
+        if (j < s) {
+            uint64_t kj = keys[j];
+            p = pos[j];
+            bool head = true;
+            if (j == 0) {
+                lcp[0] = 0;
+            } else {
+                uint64_t kp = keys[j - 1];
+                head = ((kp ^ kj) & kFast2CmpMask) != 0;
+                if (!head) {
+                    lcp[j] = kLcpPending;
+                } else if (((kp | kj) & 1ull) == 0) {
+                    lcp[j] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
+                } else if (kj == ~0ull || kp == ~0ull) {
+                    lcp[j] = 0;  // sentinel of a filtered suffix: dropped later
+                } else {
+                    lcp[j] = (uint32_t)lcp_direct(ks, pos[j - 1], p, 0);
+                }
+            }
+            active = !head || (j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, active);
+        if (m) {
+            int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(act_count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (active) {
+                unsigned long long idx = base + __popc(m & lt_mask);
+                if (idx < capacity) {
+                    act_slot[idx] = (uint32_t)j;
+                    act_pos[idx] = p;
+                }
+            }
+        }
+    }
+}
+
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
 // previous SA slot's key
 struct SparseSegIn {
     const uint64_t* keys;
     const uint32_t* slot;
+    uint64_t cmp_mask;
     __device__ uint32_t operator()(uint64_t a) const {
         uint32_t j = slot[a];
-        return (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+        return (j == 0 || ((keys[j] ^ keys[j - 1]) & cmp_mask) != 0) ? 1u : 0u;
     }
 };
 struct SparseSegOut {
@@ -300,9 +391,11 @@ struct ActiveIn {
     View v;
     uint64_t m;
     int final_word;
+    int sentinel;  // filtered suffixes ride along with key ~0 (only with packings that leave a low bit unused)
     __device__ unsigned long long operator()(uint64_t i) const {
         if (final_word) return 0;
         uint64_t ki = v.k(i);
+        if (sentinel && v.raw(i) == ~0ull) return 0;  // never refined
         bool head = !v.same_seg(i) || v.k(i - 1) != ki;
         bool next_same = (i + 1 < m) && v.same_seg(i + 1) && v.k(i + 1) == ki;
         bool active = !head || next_same;
@@ -326,7 +419,7 @@ struct ActiveOut {
 };
 
 // Next key word of every active element, packed with (segment, position) as the sort payload.
-__global__ void __launch_bounds__(kBlock) active_keys_kernel(KeySpec ks, uint64_t m, uint32_t word,
+__global__ void __launch_bounds__(kBlock) active_keys_kernel(KeySpec ks, uint64_t m, uint32_t word, int filter,
                                                              const uint32_t* __restrict__ pos,
                                                              const uint32_t* __restrict__ seg,
                                                              uint64_t* __restrict__ keys,
@@ -334,7 +427,7 @@ __global__ void __launch_bounds__(kBlock) active_keys_kernel(KeySpec ks, uint64_
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
         uint32_t p = pos[a];
-        keys[a] = key_word(ks, p, word);
+        keys[a] = (filter && !indexed_byte(ks.text[p])) ? ~0ull : key_word(ks, p, word);
         segpos[a] = ((uint64_t)seg[a] << 32) | p;
     }
 }

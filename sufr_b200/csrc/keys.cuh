@@ -34,7 +34,20 @@ struct KeySpec {
     const uint64_t* n_starts;
     const uint64_t* n_ends;
     uint32_t num_n_ranges;
+    // 2-bit fast path of the first sort (full sort of DNA-like texts); see first_key()
+    int fast2;
+    const uint64_t* packed2;   // 2 bits per symbol, 32 per word: rank among the 4 regular bytes, or the class of an irregular byte
+    const uint64_t* irr;       // 1 bit per symbol, 64 per word: symbol is not one of the 4 regular bytes (or is beyond the text)
+    const uint8_t* text;       // transformed text
+    const uint8_t* cls;        // [256] byte -> number of regular bytes smaller than it (0..4); regular bytes: their rank
 };
+
+// Fast-path keys: bit 0 = the key contains fill (an irregular symbol inside its 31-symbol window),
+// bits 63..2 = 31 symbols.  Only the top kFast2SortBits are sorted; everything that ties on them is
+// re-sorted by the exact 3-bit key words.
+constexpr int kFast2Symbols = 31;
+constexpr int kFast2SortBits = 40;
+constexpr uint64_t kFast2CmpMask = ~0ull << (64 - kFast2SortBits);
 
 __device__ __forceinline__ void split_pos(const PackedText& pt, uint64_t p, uint64_t& q, uint32_t& r) {
     if (pt.n <= 0xFFFFFFFFull) {
@@ -93,6 +106,35 @@ __device__ __forceinline__ uint64_t key_word(const KeySpec& ks, uint64_t p, uint
     return x;
 }
 
+// First sort key of suffix p on the 2-bit fast path.  Let r0 < r1 < r2 < r3 be the regular bytes.  Regular
+// symbols are coded by their rank.  The first irregular symbol x (or the end of the text) is coded
+// min(c, 3) with c = #{regular bytes < x} and every later position is FILL: zeros when c <= 3 (x sorts before
+// every continuation of r_c), ones when c == 4 (x sorts after every continuation of r3).  This keeps
+// key(a) <= key(b) whenever suffix a < suffix b, so sorting by the key is consistent with the suffix order
+// and only ties need the exact comparison.
+__device__ __forceinline__ uint64_t first_key_fast2(const KeySpec& ks, uint64_t p) {
+    const uint64_t n = ks.pt.n;
+    uint64_t q = p >> 5;
+    uint32_t r = (uint32_t)(p & 31);
+    uint64_t w0 = __ldg(ks.packed2 + q);
+    uint64_t w = r ? ((w0 << (2 * r)) | (__ldg(ks.packed2 + q + 1) >> (64 - 2 * r))) : w0;
+    uint64_t q2 = p >> 6;
+    uint32_t r2 = (uint32_t)(p & 63);
+    uint64_t m0 = __ldg(ks.irr + q2);
+    uint64_t m = r2 ? ((m0 << r2) | (__ldg(ks.irr + q2 + 1) >> (64 - r2))) : m0;
+    m &= ~0ull << (64 - kFast2Symbols);
+    w &= ~3ull;
+    if (m == 0) return w;
+    uint32_t j = (uint32_t)__clzll((long long)m);  // first irregular symbol of the window
+    uint32_t c = (p + j < n) ? ks.cls[ks.text[p + j]] : 0u;
+    uint64_t keep = ~0ull << (62 - 2 * j);           // symbols 0..j (symbol j already holds min(c, 3))
+    uint64_t key = w & keep;
+    if (c == 4) key |= ~keep & ~3ull;
+    return key | 1ull;
+}
+
+__device__ __forceinline__ uint64_t first_key(const KeySpec& ks, uint64_t p);
+
 // Number of symbols that exist in the key of suffix p.
 __device__ __forceinline__ uint64_t key_len(const KeySpec& ks, uint64_t p) {
     uint64_t rest = ks.pt.n - p;
@@ -118,6 +160,10 @@ __device__ __forceinline__ uint32_t lcp_from_words(const KeySpec& ks, uint64_t x
     if (la < l) l = la;
     if (lb < l) l = lb;
     return (uint32_t)l;
+}
+
+__device__ __forceinline__ uint64_t first_key(const KeySpec& ks, uint64_t p) {
+    return ks.fast2 ? first_key_fast2(ks, p) : key_word(ks, p, 0);
 }
 
 // If p lies in a recorded run of N, returns true and the run's end (find_n_run, sufr_builder.rs:241-254).

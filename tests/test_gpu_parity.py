@@ -361,3 +361,67 @@ def test_baseline_configs_small_vs_oracle(S, name, size, kw):
     assert check_positions(got.text, got.sa, is_dna=flags.get("is_dna", False),
                            allow_ambiguity=flags.get("allow_ambiguity", False))
     got.free()
+
+
+def dna_with_rare(rng, n, rare=b"N%RYnacgt", rare_p=0.01, repeat_p=0.02, max_rep=200, runs=True):
+    """DNA-like text: four dominant bytes plus rare irregular ones, repeats, and homopolymer runs (keys that
+    are all zeros / all ones on the 2-bit fast path)."""
+    out = bytearray()
+    while len(out) < n:
+        x = rng.random()
+        if out and x < repeat_p:
+            s = rng.randrange(len(out))
+            out += out[s:s + rng.randrange(1, max_rep)]
+        elif x < repeat_p + rare_p:
+            out.append(rng.choice(rare))
+        elif runs and x < repeat_p + rare_p + 0.002:
+            out += bytes([rng.choice(b"AT")]) * rng.randrange(20, 120)
+        else:
+            out.append(rng.choice(b"ACGT"))
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("n", [5000, 70000, 300000])
+@pytest.mark.parametrize("flags", [dict(is_dna=True), dict(is_dna=True, allow_ambiguity=True),
+                                   dict(is_dna=True, ignore_softmask=True), dict()],
+                         ids=["dna", "amb", "soft", "nodna"])
+@pytest.mark.parametrize("tail", [b"$", b"", b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"])
+def test_fast2_path_matches_oracle(S, n, flags, tail, monkeypatch):
+    """2-bit fast path of the first sort (DNA-like alphabets): irregular symbols become fill + exact ties."""
+    rng = random.Random(seed_of(n, sorted(flags), tail))
+    text = dna_with_rare(rng, n) + tail
+    gpu_vs_oracle(S, text, **flags)
+    # and the general 3-bit path gives the same answer
+    monkeypatch.setenv("SUFR_B200_DEBUG_NO_FAST2", "1")
+    gpu_vs_oracle(S, text, **flags)
+
+
+def test_fast2_many_filtered_uses_compaction(S):
+    rng = random.Random(17)
+    text = dna_with_rare(rng, 120000, rare=b"N", rare_p=0.06) + b"$"
+    gpu_vs_oracle(S, text, is_dna=True)
+
+
+def test_fast2_symbols_above_t_and_below_a(S):
+    rng = random.Random(23)
+    text = dna_with_rare(rng, 90000, rare=b"#+BDHKVWXYZ[", rare_p=0.02) + b"$"
+    gpu_vs_oracle(S, text)
+    gpu_vs_oracle(S, text, is_dna=True, allow_ambiguity=True)
+
+
+def test_fast2_deep_repeats_and_shards(S):
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = random.Random(29)
+    text = dna_with_rare(rng, 40000) + b"ACGGT" * 3000 + dna_with_rare(rng, 20000) + b"T" * 5000 + b"$"
+    _, _, doubling = gpu_vs_oracle(S, text, is_dna=True)
+    assert doubling > 0
+    want = O.oracle_build(text, is_dna=True, threads=4)
+    for world in (2, 5):
+        shards = [S.build(S.SufrBuilderArgs(text=text, is_dna=True), rank=r, world_size=world) for r in range(world)]
+        meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+        for r, s in enumerate(shards):
+            prev = previous_last_suffix(meta, r)
+            if prev is not None and s.num_suffixes:
+                s.patch_seam(prev)
+        assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
+        assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
