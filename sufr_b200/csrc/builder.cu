@@ -675,6 +675,11 @@ void Build::sort_phase(bool prefilter, bool sharded) {
     make_keys_and_sort(keys_sorted, prefilter, sharded);
     t_sorted_mark = timer.mark();
     refine(keys_sorted);
+    if (ks.fast2 && s) {
+        lcp_fixup_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+    }
 }
 
 void Build::run(SufrB200Result* out) {

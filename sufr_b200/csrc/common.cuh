@@ -34,6 +34,10 @@ inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 //   kLcpPending        : element is not a group head yet (shares all words so far with its predecessor)
 //   kLcpLowerBound | h : boundary created by a prefix-doubling round; true LCP is in [h, 2h)
 constexpr uint32_t kLcpPending = 0xFFFFFFFFu;
+//   kLcpFixup          : group boundary of the 2-bit fast path whose LCP cannot be read off the keys (a key with
+//                        fill, or a neighbouring group that is still being refined): computed exactly from the
+//                        final order once the refinement is done
+constexpr uint32_t kLcpFixup = 0xFFFFFFFEu;
 constexpr uint32_t kLcpLowerBound = 0x80000000u;
 
 }  // namespace sufr

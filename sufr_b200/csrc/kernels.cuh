@@ -341,12 +341,15 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
                 head = ((kp ^ kj) & kFast2CmpMask) != 0;
                 if (!head) {
                     lcp[j] = kLcpPending;
-                } else if (((kp | kj) & 1ull) == 0) {
-                    lcp[j] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
-                } else if (kj == ~0ull || kp == ~0ull) {
-                    lcp[j] = 0;  // sentinel of a filtered suffix: dropped later
                 } else {
-                    lcp[j] = (uint32_t)lcp_direct(ks, pos[j - 1], p, 0);
+                    // The LCP of a boundary can be read off the two keys only if neither contains fill and the
+                    // final neighbours are already known, i.e. both adjacent groups are singletons.
+                    bool next_same = j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0;
+                    bool prev_multi = j >= 2 && ((keys[j - 2] ^ kp) & kFast2CmpMask) == 0;
+                    if (((kp | kj) & 1ull) == 0 && !next_same && !prev_multi)
+                        lcp[j] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
+                    else
+                        lcp[j] = kLcpFixup;
                 }
             }
             active = !head || (j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0);
@@ -366,6 +369,14 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
             }
         }
     }
+}
+
+// Exact LCP of the boundaries the fast path could not read off the keys, from the FINAL suffix order.
+__global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
+                                                           uint32_t* __restrict__ lcp) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride)
+        if (lcp[j] == kLcpFixup) lcp[j] = j ? (uint32_t)lcp_direct(ks, sa[j - 1], sa[j], 0) : 0u;
 }
 
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
