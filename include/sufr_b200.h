@@ -89,8 +89,9 @@ typedef struct SufrB200Result {
     uint32_t memory;          /* SUFR_B200_MEM_HOST (pinned) or SUFR_B200_MEM_DEVICE */
     uint64_t text_len;
     uint64_t num_suffixes;    /* suffixes in THIS shard (== total_suffixes when world_size == 1) */
-    uint64_t total_suffixes;  /* SufrBuilder.num_suffixes over all shards */
-    uint64_t shard_offset;    /* rank of this shard's first suffix in the whole suffix array */
+    uint64_t total_suffixes;  /* SufrBuilder.num_suffixes over all shards.  Sharded full sorts balance the shards on a */
+    uint64_t shard_offset;    /*   sampled histogram: then these two are (num_suffixes, 0) and the CALLER overwrites them with */
+                              /*   the sum / prefix sum of the ranks' num_suffixes (the same exchange the seam repair needs) */
     uint64_t first_suffix;    /* SA[0] / SA[num_suffixes-1] of this shard: inputs of the seam repair */
     uint64_t last_suffix;     /*   (sufr_builder.rs:893-902); undefined when num_suffixes == 0 */
     uint8_t* text;            /* transformed text (SufrBuilder.text), text_len bytes */

@@ -264,6 +264,11 @@ class BuildResult:
         """(text, sa, lcp) raw device addresses of a device result."""
         return int(self.c.text or 0), int(self.c.sa or 0), int(self.c.lcp or 0)
 
+    def set_shard_layout(self, shard_offset: int, total_suffixes: int):
+        """Sharded builds: position of this shard in the whole suffix array (from the ranks' counts)."""
+        self.c.shard_offset = shard_offset
+        self.c.total_suffixes = total_suffixes
+
     def patch_seam(self, prev_last_suffix: int):
         _check(_lib.lib().sufr_b200_patch_seam(self._ctx.handle, C.byref(self._cargs.c), C.byref(self.c),
                                                prev_last_suffix))

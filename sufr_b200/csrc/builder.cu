@@ -164,6 +164,7 @@ class Build {
     DevBuf<uint32_t> d_isa;     // inverse suffix array (only when prefix doubling ran)
     DevBuf<uint32_t> d_counts;  // radix sort count matrix
     uint64_t shard_offset = 0, shard_count = 0, total_suffixes = 0;
+    bool layout_exact_ = true;  // shard_offset / total_suffixes are known without an exchange
     bool full_set_ = true;  // every text position is being sorted on this rank (prefix doubling needs that)
     int t_keys_mark = -1, t_sorted_mark = -1;
     rsort::EventPairs downsweep_events;
@@ -335,15 +336,22 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     const int world = args.world_size > 1 ? args.world_size : 1;
     uint64_t lo = 0, hi = 0;
     shard_offset = 0;
+    layout_exact_ = world == 1;
+    uint64_t shard_estimate = 0;
     if (world > 1) {
         // Splitters from a histogram of the top 12 key bits: every rank computes the same histogram of the
-        // replicated text, so ranks agree on the key ranges without communicating.
+        // replicated text, so ranks agree on the key ranges without communicating.  The full sort only needs
+        // balanced ranges, so it histograms every 16th position; the modes whose tie order depends on the
+        // input order (mask / max-query-len) and the slicing fallback use the exact histogram, which also
+        // yields the exact shard offsets.
         const uint32_t hbits = 12, bins = 1u << hbits;
+        const bool exact = ks.mode != kModeFull || !sharded;
+        const uint32_t sample_shift = exact ? 0 : 4;
         auto d_hist = dalloc<unsigned long long>(bins);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_hist.get(), 0, bins * 8, st()));
         if (n) {
-            key_hist_kernel<<<grid_for(n, 8), kBlock, bins * sizeof(uint32_t), st()>>>(
-                ks, n, hbits, d_text.get(), filter_active ? 1 : 0, d_hist.get());
+            key_hist_kernel<<<grid_for(n >> sample_shift, 8), kBlock, bins * sizeof(uint32_t), st()>>>(
+                ks, n, hbits, d_text.get(), filter_active ? 1 : 0, sample_shift, d_hist.get());
             SUFR_KERNEL_CHECK();
             launched();
         }
@@ -362,10 +370,17 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             while (g < world && acc * world >= total * g) cut[g++] = b + 1;
         }
         uint32_t b0 = cut[args.rank], b1 = cut[args.rank + 1];
-        total_suffixes = total;
-        for (uint32_t b = 0; b < b0; b++) shard_offset += hist[b];
-        shard_count = 0;
-        for (uint32_t b = b0; b < b1; b++) shard_count += hist[b];
+        unsigned long long before = 0, mine = 0;
+        for (uint32_t b = 0; b < b0; b++) before += hist[b];
+        for (uint32_t b = b0; b < b1; b++) mine += hist[b];
+        if (exact) {
+            total_suffixes = total;
+            shard_offset = before;
+            shard_count = mine;
+            layout_exact_ = true;
+        } else {
+            shard_estimate = mine << sample_shift;
+        }
         lo = (uint64_t)b0 << (64 - hbits);
         hi = b1 >= bins ? 0 : (uint64_t)b1 << (64 - hbits);
         if (b0 >= b1) { lo = ~0ull; hi = ~0ull; }  // empty shard: [max, max) selects nothing
@@ -391,7 +406,32 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     // key ~0 and drop off the end of the sorted array.  Needs an unused low bit in the packed word.
     const bool sentinel = prefilter && !sharded && used_bits < 64 && (n - kept) * 16 <= n;
     sentinel_ = sentinel;
-    if (sharded || (prefilter && !sentinel)) {
+    if (sharded && ks.mode == kModeFull) {
+        // unordered selection: one key computation per position, capacity from the sampled histogram
+        uint64_t capacity = shard_estimate + shard_estimate / 16 + (1u << 20);
+        auto d_cnt = dalloc<unsigned long long>(1);
+        for (int attempt = 0;; attempt++) {
+            keys_a = dalloc<uint64_t>(capacity);
+            pos_a = dalloc<uint32_t>(capacity);
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
+            if (n) {
+                select_append_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
+                                                                         pos_a.get(), d_cnt.get(), capacity);
+                SUFR_KERNEL_CHECK();
+                launched();
+            }
+            unsigned long long c = 0;
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(&c, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            s = c;
+            if (c <= capacity) break;
+            if (attempt) throw Error(SUFR_B200_ERR_INTERNAL, "shard selection overflowed twice");
+            keys_a.reset();
+            pos_a.reset();
+            capacity = c;
+        }
+        sort_n = s;
+    } else if (sharded || (prefilter && !sentinel)) {
         SelectIn in{ks, n, descending, sharded ? 1 : 0, lo, hi, d_text.get(), prefilter ? 1 : 0};
         s = sharded ? shard_count : kept;  // both exact: histogram of indexed suffixes / indexed count
         keys_a = dalloc<uint64_t>(s);
@@ -795,8 +835,10 @@ void Build::run(SufrB200Result* out) {
         s = shard_count;
     }
 
-    // shard bookkeeping
+    // shard bookkeeping: without an exact histogram the caller fills shard_offset / total_suffixes after the
+    // (count, first, last) exchange it needs for the seam repair anyway
     if (args.world_size <= 1) total_suffixes = s;
+    else if (!layout_exact_) { total_suffixes = s; shard_offset = 0; }
     uint64_t first = 0, last = 0;
     if (s) {
         uint32_t fl[2];

@@ -192,17 +192,57 @@ struct SelectOut {
 };
 
 
+// Full sort only (the order of equal keys is irrelevant there): UNORDERED selection of this rank's suffixes,
+// one key computation per position and no scan.  `count` keeps counting past `capacity`.
+__global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint64_t n, uint64_t lo, uint64_t hi,
+                                                               int filter, uint64_t* __restrict__ keys,
+                                                               uint32_t* __restrict__ pos,
+                                                               unsigned long long* __restrict__ count,
+                                                               uint64_t capacity) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); p0 < n; p0 += stride) {
+        const uint64_t p = p0 + lane;
+        bool take = false;
+        uint64_t k = 0;
+        if (p < n && (!filter || indexed_byte(ks.text[p]))) {
+            k = first_key(ks, p);
+            take = k >= lo && (hi == 0 || k < hi);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+            int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (take) {
+                unsigned long long idx = base + __popc(m & lt_mask);
+                if (idx < capacity) {
+                    keys[idx] = k;
+                    pos[idx] = (uint32_t)p;
+                }
+            }
+        }
+    }
+}
+
 // Histogram of the top `hbits` bits of the first key word over the indexed suffixes (splitter selection).
+// With sample_shift > 0 only every 2^sample_shift-th position is counted (enough to balance the shards).
 __global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n, uint32_t hbits,
                                                           const uint8_t* __restrict__ text, int filter,
+                                                          uint32_t sample_shift,
                                                           unsigned long long* __restrict__ hist) {
     extern __shared__ uint32_t sh[];
     const uint32_t bins = 1u << hbits;
     for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    const uint64_t ns = (n + ((1ull << sample_shift) - 1)) >> sample_shift;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += stride) {
+        uint64_t p = i << sample_shift;
         if (!filter || indexed_byte(text[p])) atomicAdd(&sh[(uint32_t)(first_key(ks, p) >> (64 - hbits))], 1u);
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);

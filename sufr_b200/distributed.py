@@ -49,9 +49,7 @@ def finish_shard(result, group=None):
     rank = dist.get_rank(group)
     meta = gather_meta(result.num_suffixes, result.first_suffix, result.last_suffix, group)
     offs, total = shard_layout(meta)
-    if total != result.total_suffixes or offs[rank] != result.shard_offset:
-        raise RuntimeError(f"shard layout mismatch on rank {rank}: gathered ({offs[rank]}, {total}) vs "
-                           f"local ({result.shard_offset}, {result.total_suffixes})")
+    result.set_shard_layout(offs[rank], total)
     prev = previous_last_suffix(meta, rank)
     if prev is not None and result.num_suffixes:
         result.patch_seam(prev)

@@ -235,7 +235,7 @@ def test_key_range_shards_concatenate(S, world, kw):
     offs, total = shard_layout(meta)
     assert total == want.num_suffixes
     for r, s in enumerate(shards):
-        assert s.total_suffixes == total and s.shard_offset == offs[r]
+        s.set_shard_layout(offs[r], total)
         prev = previous_last_suffix(meta, r)
         if prev is not None and s.num_suffixes:
             s.patch_seam(prev)
@@ -309,7 +309,7 @@ def test_sharded_deep_repeats_fall_back_to_full_sort(S, world):
         offs, total = shard_layout(meta)
         assert total == want.num_suffixes
         for r, s in enumerate(shards):
-            assert s.total_suffixes == total and s.shard_offset == offs[r]
+            s.set_shard_layout(offs[r], total)
             prev = previous_last_suffix(meta, r)
             if prev is not None and s.num_suffixes:
                 s.patch_seam(prev)
@@ -425,3 +425,26 @@ def test_fast2_deep_repeats_and_shards(S):
                 s.patch_seam(prev)
         assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
         assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
+
+
+def test_sharded_build_writes_one_file(S, tmp_path):
+    """Every rank pwrites its slice into the same `.sufr` (sufr_b200_write, sharded): byte-identical to the
+    single-process file."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = random.Random(31)
+    text = dna_with_rare(rng, 150000) + b"$"
+    single = tmp_path / "single.sufr"
+    S.SufrBuilder(S.SufrBuilderArgs(text=text, path=str(single), is_dna=True, sequence_names=["x"]), 32)
+    out = tmp_path / "sharded.sufr"
+    world = 4
+    args = S.SufrBuilderArgs(text=text, path=str(out), is_dna=True, sequence_names=["x"])
+    shards = [S.build(args, rank=r, world_size=world) for r in range(world)]
+    meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+    offs, total = shard_layout(meta)
+    for r, s in enumerate(shards):
+        s.set_shard_layout(offs[r], total)
+        prev = previous_last_suffix(meta, r)
+        if prev is not None and s.num_suffixes:
+            s.patch_seam(prev)
+        s.write()
+    assert out.read_bytes() == single.read_bytes()
