@@ -415,7 +415,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             pos_a = dalloc<uint32_t>(capacity);
             SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
             if (n) {
-                select_append_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
+                select_append_kernel<<<grid_for(n, kSelectRows), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
                                                                          pos_a.get(), d_cnt.get(), capacity);
                 SUFR_KERNEL_CHECK();
                 launched();

@@ -193,37 +193,61 @@ struct SelectOut {
 
 
 // Full sort only (the order of equal keys is irrelevant there): UNORDERED selection of this rank's suffixes,
-// one key computation per position and no scan.  `count` keeps counting past `capacity`.
+// one key computation per position and no device-wide scan.  A block compacts a chunk of 2048 positions with
+// warp ballots and reserves its output range with ONE global atomic.  `count` keeps counting past `capacity`.
+constexpr int kSelectRows = 8;
 __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint64_t n, uint64_t lo, uint64_t hi,
                                                                int filter, uint64_t* __restrict__ keys,
                                                                uint32_t* __restrict__ pos,
                                                                unsigned long long* __restrict__ count,
                                                                uint64_t capacity) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
+    constexpr int WARPS = kBlock / 32;
+    __shared__ uint32_t wcount[kSelectRows * WARPS];
+    __shared__ unsigned long long gbase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); p0 < n; p0 += stride) {
-        const uint64_t p = p0 + lane;
-        bool take = false;
-        uint64_t k = 0;
-        if (p < n && (!filter || indexed_byte(ks.text[p]))) {
-            k = first_key(ks, p);
-            take = k >= lo && (hi == 0 || k < hi);
+    const uint64_t chunk = (uint64_t)kBlock * kSelectRows;
+    const uint64_t chunks = (n + chunk - 1) / chunk;
+    for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+        uint64_t k[kSelectRows];
+        uint32_t lidx[kSelectRows];
+        uint32_t takes = 0;
+#pragma unroll
+        for (int r = 0; r < kSelectRows; r++) {
+            const uint64_t p = c * chunk + (uint64_t)r * kBlock + threadIdx.x;
+            bool take = false;
+            k[r] = 0;
+            if (p < n && (!filter || indexed_byte(ks.text[p]))) {
+                k[r] = first_key(ks, p);
+                take = k[r] >= lo && (hi == 0 || k[r] < hi);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, take);
+            lidx[r] = __popc(m & lt_mask);
+            if (lane == 0) wcount[r * WARPS + warp] = __popc(m);
+            takes |= (take ? 1u : 0u) << r;
         }
-        unsigned m = __ballot_sync(0xffffffffu, take);
-        if (m) {
-            int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (take) {
-                unsigned long long idx = base + __popc(m & lt_mask);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int i = 0; i < kSelectRows * WARPS; i++) {
+                uint32_t t = wcount[i];
+                wcount[i] = acc;
+                acc += t;
+            }
+            gbase = acc ? atomicAdd(count, (unsigned long long)acc) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kSelectRows; r++) {
+            if (takes & (1u << r)) {
+                unsigned long long idx = gbase + wcount[r * WARPS + warp] + lidx[r];
                 if (idx < capacity) {
-                    keys[idx] = k;
-                    pos[idx] = (uint32_t)p;
+                    keys[idx] = k[r];
+                    pos[idx] = (uint32_t)(c * chunk + (uint64_t)r * kBlock + threadIdx.x);
                 }
             }
         }
+        __syncthreads();
     }
 }
 
