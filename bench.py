@@ -368,7 +368,7 @@ def run_e2e(args, S, ctx, d_text, text_len, bargs, rank, world, dev, barrier):
     tot = 0
     for _ in range(args.e2e_steps):
         r = step()
-        d2h = r.text_len + 2 * r.num_suffixes * (args.index_bits // 8)
+        d2h = (r.text_len if rank == 0 else 0) + 2 * r.num_suffixes * (args.index_bits // 8)
         tot = r.total_suffixes
         _ = int(r.sa[:1024].sum()) if r.num_suffixes else 0  # read the step's result on the host
         r.free()

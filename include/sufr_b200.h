@@ -94,7 +94,7 @@ typedef struct SufrB200Result {
                               /*   the sum / prefix sum of the ranks' num_suffixes (the same exchange the seam repair needs) */
     uint64_t first_suffix;    /* SA[0] / SA[num_suffixes-1] of this shard: inputs of the seam repair */
     uint64_t last_suffix;     /*   (sufr_builder.rs:893-902); undefined when num_suffixes == 0 */
-    uint8_t* text;            /* transformed text (SufrBuilder.text), text_len bytes */
+    uint8_t* text;            /* transformed text (SufrBuilder.text), text_len bytes; NULL in HOST results of ranks > 0 */
     void* sa;                 /* num_suffixes elements of index_bits */
     void* lcp;                /* num_suffixes elements; lcp[0] of shard > 0 needs sufr_b200_patch_seam */
     uint64_t* n_ranges;       /* host: num_n_ranges pairs [start, end) (SufrBuilder.n_ranges) */

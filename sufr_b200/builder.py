@@ -227,6 +227,8 @@ class BuildResult:
 
     @property
     def text(self) -> bytes:
+        if not self.c.text:
+            raise SufrError(_lib.ERR_ARGUMENT, "the transformed text is only returned on rank 0 of a sharded build")
         return self._np(self.c.text, self.text_len, np.uint8).tobytes()
 
     @property

@@ -902,11 +902,13 @@ void Build::run(SufrB200Result* out) {
         }
     } else {
         int e0 = timer.mark();
-        owner->text = ctx.pinned.get(n);
+        // sharded builds: only rank 0 returns the transformed text (it writes the text section of the file)
+        const bool want_text = args.world_size <= 1 || args.rank == 0;
+        owner->text = want_text ? ctx.pinned.get(n) : nullptr;
         owner->sa = ctx.pinned.get(s * w);
         owner->lcp = ctx.pinned.get(s * w);
         int e1 = timer.mark();
-        if (n) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
+        if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
         if (s) {
             SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa_out, s * w, cudaMemcpyDeviceToHost, st()));
             SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->lcp, d_lcp_out, s * w, cudaMemcpyDeviceToHost, st()));
@@ -1101,36 +1103,44 @@ int sufr_b200_patch_seam(SufrB200Ctx* c, const SufrB200Args* args, SufrB200Resul
         const uint64_t a = prev_last_suffix, b = r->first_suffix, n = r->text_len;
         if (a >= n || b >= n) throw Error(SUFR_B200_ERR_ARGUMENT, "suffix out of range");
         uint64_t l = 0;
-        if (r->memory == SUFR_B200_MEM_HOST) {
-            l = host_pair_lcp(r->text, n, a, b, has_mask ? &mask : nullptr, q, r->n_ranges, r->num_n_ranges);
+        // Windows of the two suffixes in TRANSFORMED form, from wherever the text is at hand: the host result,
+        // the device result, or (host results of ranks > 0 carry no text) the caller's raw text + the transform.
+        auto fetch = [&](uint64_t p, uint64_t len, uint8_t* dst) {
+            if (r->text && r->memory == SUFR_B200_MEM_HOST) {
+                memcpy(dst, r->text + p, len);
+            } else if (r->text) {
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(dst, r->text + p, len, cudaMemcpyDeviceToHost, ctx->stream));
+                SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            } else {
+                if (!args->text) throw Error(SUFR_B200_ERR_ARGUMENT, "patch_seam needs the text (result or args)");
+                for (uint64_t i = 0; i < len; i++) {  // sufr_builder.rs:149-156
+                    uint8_t c = args->text[p + i];
+                    if (c >= 97 && c <= 122) c = args->ignore_softmask ? (uint8_t)'N' : (uint8_t)(c & 0x5F);
+                    dst[i] = c;
+                }
+            }
+        };
+        auto in_run = [&](uint64_t p, uint64_t& end) {
+            uint64_t lo = 0, hi = r->num_n_ranges;
+            while (lo < hi) {
+                uint64_t mid = (lo + hi) / 2;
+                if (r->n_ranges[2 * mid] <= p && p < r->n_ranges[2 * mid + 1]) { end = r->n_ranges[2 * mid + 1]; return true; }
+                if (r->n_ranges[2 * mid] < p) lo = mid + 1; else hi = mid;
+            }
+            return false;
+        };
+        uint64_t ea = 0, eb = 0;
+        if (!has_mask && r->num_n_ranges && in_run(a, ea) && in_run(b, eb)) {
+            l = std::min(ea - a, eb - b);  // sufr_builder.rs:305-307
         } else {
-            // Device result: compare growing windows of the two suffixes on the host (the two suffixes come
-            // from different key ranges, so they almost always differ within the first few bytes).
+            // the two suffixes come from different key ranges, so they differ within the first few symbols;
+            // the window grows if they do not
             uint64_t win = has_mask ? mask.bytes.size() + 64 : 4096;
             while (true) {
                 uint64_t la = std::min(win, n - a), lb = std::min(win, n - b);
                 std::vector<uint8_t> buf(la + lb);
-                SUFR_CUDA_CHECK(cudaMemcpyAsync(buf.data(), r->text + a, la, cudaMemcpyDeviceToHost, ctx->stream));
-                SUFR_CUDA_CHECK(cudaMemcpyAsync(buf.data() + la, r->text + b, lb, cudaMemcpyDeviceToHost, ctx->stream));
-                SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-                // rebase: the window of suffix a is buf[0, la), of suffix b is buf[la, la + lb)
-                uint64_t ea = 0, eb = 0;
-                bool both_n = false;
-                if (!has_mask && r->num_n_ranges) {
-                    // N-run shortcut needs only the recorded ranges
-                    uint64_t lo = 0, hi = r->num_n_ranges;
-                    auto find = [&](uint64_t p, uint64_t& end) {
-                        lo = 0; hi = r->num_n_ranges;
-                        while (lo < hi) {
-                            uint64_t mid = (lo + hi) / 2;
-                            if (r->n_ranges[2 * mid] <= p && p < r->n_ranges[2 * mid + 1]) { end = r->n_ranges[2 * mid + 1]; return true; }
-                            if (r->n_ranges[2 * mid] < p) lo = mid + 1; else hi = mid;
-                        }
-                        return false;
-                    };
-                    both_n = find(a, ea) && find(b, eb);
-                }
-                if (both_n) { l = std::min(ea - a, eb - b); break; }
+                fetch(a, la, buf.data());
+                fetch(b, lb, buf.data() + la);
                 if (has_mask) {
                     l = 0;
                     for (uint64_t k = 0; k < mask.positions.size(); k++) {
