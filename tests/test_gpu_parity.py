@@ -448,3 +448,28 @@ def test_sharded_build_writes_one_file(S, tmp_path):
             s.patch_seam(prev)
         s.write()
     assert out.read_bytes() == single.read_bytes()
+
+
+@pytest.mark.parametrize("golden,fasta,flags", [c for c in GOLDEN_CASES if c[0] in
+                                                ("1.sufr", "2d.sufr", "2ns.sufr", "long_dna_sequence_allow_ambiguity.sufr",
+                                                 "uniprot-masked.sufr", "abba.sufr")], ids=lambda v: v if isinstance(v, str) else "")
+def test_cli_create_writes_golden_files(tmp_path, golden, fasta, flags):
+    """`sufr-b200 create` with the reference's flags (sufr/tests/cli.rs:55-302) -> byte-identical `.sufr`."""
+    import subprocess
+    exe = __import__("conftest").ROOT / "sufr_b200" / "sufr-b200"
+    out = tmp_path / golden
+    cmd = [str(exe), "create", "-o", str(out), str(GOLDEN / "inputs" / fasta)]
+    if flags.get("is_dna"):
+        cmd.append("--dna")
+    if flags.get("allow_ambiguity"):
+        cmd.append("--allow-ambiguity")
+    if flags.get("ignore_softmask"):
+        cmd.append("--ignore-softmask")
+    if "delimiter" in flags:
+        cmd += ["--sequence-delimiter", flags["delimiter"].decode()]
+    if "seed_mask" in flags:
+        cmd += ["--seed-mask", flags["seed_mask"]]
+    r = subprocess.run(cmd + ["--log", "info"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Sorted" in r.stdout
+    assert out.read_bytes() == (GOLDEN / "expected" / golden).read_bytes()
