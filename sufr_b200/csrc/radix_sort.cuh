@@ -140,15 +140,20 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
         __syncthreads();
 
         // warp-level ranking: items are visited in tile order (warp, i, lane) => stable
-        if (count == (uint32_t)TILE) {
-            // full tile: every lane is valid, no validity vote and no divergence
 #pragma unroll
-            for (int i = 0; i < IPT; i++) {
-                uint32_t d = digit_of(key[i], shift, dmask);
-                unsigned peers = 0xffffffffu;  // lanes holding the same digit: one vote per digit bit
+        for (int i = 0; i < IPT; i++) {
+            uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
+            bool valid = idx < count;
+            uint32_t d = digit_of(key[i], shift, dmask);
+            unsigned vm = __ballot_sync(0xffffffffu, valid);
+            uint32_t r = 0;
+            if (valid) {
+                // lanes holding the same digit, by one vote per digit bit (match.any saturates the ADU pipe:
+                // profiles/r1_v0_downsweep_match_any_raw.csv)
+                unsigned peers = vm;
 #pragma unroll
                 for (int b = 0; b < RADIX_BITS; b++) {
-                    unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                    unsigned vote = __ballot_sync(vm, (d >> b) & 1u);
                     peers &= ((d >> b) & 1u) ? vote : ~vote;
                 }
                 int leader = __ffs(peers) - 1;
@@ -157,37 +162,11 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
                     old = wc[warp][d];
                     wc[warp][d] = old + __popc(peers);
                 }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                slot[i] = old + __popc(peers & lt_mask);
-                __syncwarp();
+                old = __shfl_sync(peers, old, leader);
+                r = old + __popc(peers & lt_mask);
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < IPT; i++) {
-                uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
-                bool valid = idx < count;
-                uint32_t d = digit_of(key[i], shift, dmask);
-                unsigned vm = __ballot_sync(0xffffffffu, valid);
-                uint32_t r = 0;
-                if (valid) {
-                    unsigned peers = vm;
-#pragma unroll
-                    for (int b = 0; b < RADIX_BITS; b++) {
-                        unsigned vote = __ballot_sync(vm, (d >> b) & 1u);
-                        peers &= ((d >> b) & 1u) ? vote : ~vote;
-                    }
-                    int leader = __ffs(peers) - 1;
-                    uint32_t old = 0;
-                    if (lane == leader) {
-                        old = wc[warp][d];
-                        wc[warp][d] = old + __popc(peers);
-                    }
-                    old = __shfl_sync(peers, old, leader);
-                    r = old + __popc(peers & lt_mask);
-                }
-                slot[i] = r;
-                __syncwarp();
-            }
+            slot[i] = r;
+            __syncwarp();
         }
         __syncthreads();
 
