@@ -285,6 +285,8 @@ void Build::encode(const uint8_t* d_raw) {
             launched();
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
             ks.fast2 = 1;
+            ks.packed2_words = words2 + 2;
+            ks.irr_words = words2 / 2 + 2;
             ks.packed2 = d_packed2.get();
             ks.irr = d_irr.get();
             ks.cls = d_cls.get();
@@ -415,7 +417,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             pos_a = dalloc<uint32_t>(capacity);
             SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
             if (n) {
-                select_append_kernel<<<grid_for(n, kSelectRows), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
+                select_append_kernel<<<grid_for(n, 32), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
                                                                          pos_a.get(), d_cnt.get(), capacity);
                 SUFR_KERNEL_CHECK();
                 launched();
@@ -447,8 +449,12 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         keys_a = dalloc<uint64_t>(n);
         pos_a = dalloc<uint32_t>(n);
         if (n) {
-            keygen_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, descending, d_text.get(), sentinel ? 1 : 0,
-                                                              keys_a.get(), pos_a.get());
+            if (ks.fast2 && !descending)
+                keygen_fast2_kernel<<<grid_for(n, 8), kBlock, 0, st()>>>(ks, n, sentinel ? 1 : 0, keys_a.get(),
+                                                                        pos_a.get());
+            else
+                keygen_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, descending, d_text.get(), sentinel ? 1 : 0,
+                                                                  keys_a.get(), pos_a.get());
             SUFR_KERNEL_CHECK();
             launched();
         }
@@ -802,8 +808,7 @@ void Build::run(SufrB200Result* out) {
         sliced = sharded;
         prefilter = false;
         sharded = false;
-        ctx.pool.reserve((size_t)(32 * n + (64ull << 20)));
-        sort_phase(false, false);
+        sort_phase(false, false);  // the pool was sized for an unsharded build of n positions up front
     }
     int t2 = t_sorted_mark;
     int t3 = timer.mark();

@@ -129,6 +129,27 @@ __global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, 
     }
 }
 
+// Fast-path variant of keygen_kernel: warp-window key generation (keys.cuh::Fast2Window), ascending order.
+__global__ void __launch_bounds__(kBlock) keygen_fast2_kernel(KeySpec ks, uint64_t n, int filter,
+                                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t chunks = (n + 1023) >> 10;
+    for (uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < chunks; c += warps) {
+        const uint64_t W0 = c << 10;
+        Fast2Window fw = fast2_window_load(ks, W0, lane);
+#pragma unroll 4
+        for (int r = 0; r < 32; r++) {
+            uint64_t k = fast2_window_key(ks, fw, W0, r, lane);
+            uint64_t p = W0 + (uint64_t)r * 32 + lane;
+            if (p < n) {
+                keys[p] = (filter && !indexed_byte(ks.text[p])) ? ~0ull : k;
+                pos[p] = (uint32_t)p;
+            }
+        }
+    }
+}
+
 // Number of indexed suffixes (16 bytes per load).
 __global__ void __launch_bounds__(kBlock) count_indexed_kernel(const uint8_t* __restrict__ text, uint64_t n,
                                                                unsigned long long* __restrict__ out) {
@@ -206,48 +227,52 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
     __shared__ unsigned long long gbase;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint64_t chunk = (uint64_t)kBlock * kSelectRows;
+    // a block iteration covers WARPS x 1024 positions: warp w owns [c*8192 + w*1024, +1024), 32 rows of 32
+    const uint64_t chunk = (uint64_t)WARPS * 1024;
     const uint64_t chunks = (n + chunk - 1) / chunk;
     for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
-        uint64_t k[kSelectRows];
-        uint32_t lidx[kSelectRows];
-        uint32_t takes = 0;
+        const uint64_t W0 = c * chunk + (uint64_t)warp * 1024;
+        Fast2Window fw{};
+        if (ks.fast2) fw = fast2_window_load(ks, W0, lane);
+        for (int g = 0; g < 32 / kSelectRows; g++) {
+            uint64_t k[kSelectRows];
+            uint32_t lidx[kSelectRows];
+            uint32_t takes = 0;
 #pragma unroll
-        for (int r = 0; r < kSelectRows; r++) {
-            const uint64_t p = c * chunk + (uint64_t)r * kBlock + threadIdx.x;
-            bool take = false;
-            k[r] = 0;
-            if (p < n && (!filter || indexed_byte(ks.text[p]))) {
-                k[r] = first_key(ks, p);
-                take = k[r] >= lo && (hi == 0 || k[r] < hi);
+            for (int r = 0; r < kSelectRows; r++) {
+                const int row = g * kSelectRows + r;
+                const uint64_t p = W0 + (uint64_t)row * 32 + lane;
+                uint64_t key = ks.fast2 ? fast2_window_key(ks, fw, W0, row, lane) : (p < n ? key_word(ks, p, 0) : 0ull);
+                bool take = p < n && (!filter || indexed_byte(ks.text[p])) && key >= lo && (hi == 0 || key < hi);
+                k[r] = key;
+                unsigned m = __ballot_sync(0xffffffffu, take);
+                lidx[r] = __popc(m & lt_mask);
+                if (lane == 0) wcount[r * WARPS + warp] = __popc(m);
+                takes |= (take ? 1u : 0u) << r;
             }
-            unsigned m = __ballot_sync(0xffffffffu, take);
-            lidx[r] = __popc(m & lt_mask);
-            if (lane == 0) wcount[r * WARPS + warp] = __popc(m);
-            takes |= (take ? 1u : 0u) << r;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t acc = 0;
-            for (int i = 0; i < kSelectRows * WARPS; i++) {
-                uint32_t t = wcount[i];
-                wcount[i] = acc;
-                acc += t;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t acc = 0;
+                for (int i = 0; i < kSelectRows * WARPS; i++) {
+                    uint32_t t = wcount[i];
+                    wcount[i] = acc;
+                    acc += t;
+                }
+                gbase = acc ? atomicAdd(count, (unsigned long long)acc) : 0ull;
             }
-            gbase = acc ? atomicAdd(count, (unsigned long long)acc) : 0ull;
-        }
-        __syncthreads();
+            __syncthreads();
 #pragma unroll
-        for (int r = 0; r < kSelectRows; r++) {
-            if (takes & (1u << r)) {
-                unsigned long long idx = gbase + wcount[r * WARPS + warp] + lidx[r];
-                if (idx < capacity) {
-                    keys[idx] = k[r];
-                    pos[idx] = (uint32_t)(c * chunk + (uint64_t)r * kBlock + threadIdx.x);
+            for (int r = 0; r < kSelectRows; r++) {
+                if (takes & (1u << r)) {
+                    unsigned long long idx = gbase + wcount[r * WARPS + warp] + lidx[r];
+                    if (idx < capacity) {
+                        keys[idx] = k[r];
+                        pos[idx] = (uint32_t)(W0 + (uint64_t)(g * kSelectRows + r) * 32 + lane);
+                    }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

@@ -40,6 +40,8 @@ struct KeySpec {
     const uint64_t* irr;       // 1 bit per symbol, 64 per word: symbol is not one of the 4 regular bytes (or is beyond the text)
     const uint8_t* text;       // transformed text
     const uint8_t* cls;        // [256] byte -> number of regular bytes smaller than it (0..4); regular bytes: their rank
+    uint64_t packed2_words;    // allocation sizes (bounds of the warp-window loads)
+    uint64_t irr_words;
 };
 
 // Fast-path keys: bit 0 = the key contains fill (an irregular symbol inside its 31-symbol window),
@@ -134,6 +136,39 @@ __device__ __forceinline__ uint64_t first_key_fast2(const KeySpec& ks, uint64_t 
 }
 
 __device__ __forceinline__ uint64_t first_key(const KeySpec& ks, uint64_t p);
+
+// Warp-cooperative key generation on the fast path: a warp owns 1024 consecutive positions starting at W0
+// (a multiple of 1024).  Lane l holds packed2 word W0/32 + l and (l <= 16) irr word W0/64 + l; the key of
+// position W0 + 32 r + lane is assembled from two shuffled words instead of four global loads.
+struct Fast2Window {
+    uint64_t w, w_ext, ir;
+};
+__device__ __forceinline__ Fast2Window fast2_window_load(const KeySpec& ks, uint64_t W0, int lane) {
+    Fast2Window fw;
+    uint64_t q = (W0 >> 5) + lane;
+    fw.w = q < ks.packed2_words ? __ldg(ks.packed2 + q) : 0ull;
+    uint64_t qe = (W0 >> 5) + 32;
+    fw.w_ext = qe < ks.packed2_words ? __ldg(ks.packed2 + qe) : 0ull;
+    uint64_t qi = (W0 >> 6) + lane;
+    fw.ir = (lane <= 16 && qi < ks.irr_words) ? __ldg(ks.irr + qi) : ~0ull;
+    return fw;
+}
+// r is warp-uniform
+__device__ __forceinline__ uint64_t fast2_window_key(const KeySpec& ks, const Fast2Window& fw, uint64_t W0, int r,
+                                                     int lane) {
+    uint64_t hi = __shfl_sync(0xffffffffu, fw.w, r);
+    uint64_t lo = __shfl_sync(0xffffffffu, fw.w, (r + 1) & 31);
+    if (r == 31) lo = fw.w_ext;
+    uint64_t w = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
+    uint64_t i0 = __shfl_sync(0xffffffffu, fw.ir, r >> 1);
+    uint64_t i1 = __shfl_sync(0xffffffffu, fw.ir, (r >> 1) + 1);
+    uint32_t bit = (uint32_t)(r & 1) * 32u + (uint32_t)lane;
+    uint64_t m = bit ? ((i0 << bit) | (i1 >> (64 - bit))) : i0;
+    m &= ~0ull << (64 - kFast2Symbols);
+    w &= ~3ull;
+    if (m == 0) return w;
+    return first_key_fast2(ks, W0 + (uint64_t)r * 32 + lane);  // window contains an irregular symbol (rare)
+}
 
 // Number of symbols that exist in the key of suffix p.
 __device__ __forceinline__ uint64_t key_len(const KeySpec& ks, uint64_t p) {

@@ -44,7 +44,7 @@ class DevicePool {
                     }
                 }
             }
-            add_chunk(std::max(bytes, (size_t)256 << 20));
+            add_chunk(std::max(bytes, (size_t)2 << 30));  // grow in >= 2 GB steps
         }
         throw Error(3, "device pool: allocation of " + std::to_string(bytes) + " bytes failed");
     }
