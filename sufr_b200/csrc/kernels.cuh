@@ -811,6 +811,95 @@ struct FilterLcpOut {
         scanned[j] = ord_to_lcp((uint32_t)incl);
     }
 };
+// Fast suffix filter for the common case of few, scattered non-indexed suffixes: flags by ballot, ordered
+// block-level compaction, LCP of a kept element = min over the (short) run of dropped elements before it.
+// A run longer than kFilterLookback sets `overflow` and the generic segmented-min scan takes over.
+constexpr int kFilterRows = 8;
+constexpr uint32_t kFilterLookback = 256;
+__global__ void __launch_bounds__(kBlock) filter_flags_kernel(const uint8_t* __restrict__ text,
+                                                              const uint32_t* __restrict__ sa, uint64_t s,
+                                                              uint32_t* __restrict__ flags32,
+                                                              uint32_t* __restrict__ block_counts) {
+    __shared__ uint32_t wsum[kBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kBlock * kFilterRows;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < kFilterRows; r++) {
+        uint64_t j = base + (uint64_t)r * kBlock + threadIdx.x;
+        bool keep = j < s && indexed_byte(text[sa[j]]);
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) {
+            flags32[(base + (uint64_t)r * kBlock) / 32 + warp] = m;
+            cnt += __popc(m);
+        }
+    }
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kBlock / 32; w++) t += wsum[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+struct BlockCountIn {
+    const uint32_t* counts;
+    __device__ uint32_t operator()(uint64_t b) const { return counts[b]; }
+};
+struct BlockOffsetOut {
+    uint32_t* offsets;
+    __device__ void operator()(uint64_t b, uint32_t v, uint32_t incl) const { offsets[b] = incl - v; }
+};
+__global__ void __launch_bounds__(kBlock) filter_compact_kernel(const uint32_t* __restrict__ sa,
+                                                                const uint32_t* __restrict__ lcp, uint64_t s,
+                                                                const uint32_t* __restrict__ flags32,
+                                                                const uint32_t* __restrict__ block_offsets,
+                                                                uint32_t* __restrict__ out_sa,
+                                                                uint32_t* __restrict__ out_lcp,
+                                                                uint32_t* __restrict__ overflow) {
+    constexpr int WARPS = kBlock / 32;
+    __shared__ uint32_t woff[kFilterRows * WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kBlock * kFilterRows;
+    uint32_t masks[kFilterRows];
+#pragma unroll
+    for (int r = 0; r < kFilterRows; r++) {
+        uint64_t w = (base + (uint64_t)r * kBlock) / 32 + warp;
+        masks[r] = (w * 32 < s) ? flags32[w] : 0u;
+        if (lane == 0) woff[r * WARPS + warp] = __popc(masks[r]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = block_offsets[blockIdx.x];
+        for (int i = 0; i < kFilterRows * WARPS; i++) {
+            uint32_t t = woff[i];
+            woff[i] = acc;
+            acc += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kFilterRows; r++) {
+        if (masks[r] & (1u << lane)) {
+            uint64_t j = base + (uint64_t)r * kBlock + threadIdx.x;
+            uint32_t v = lcp[j];
+            uint32_t k = 1;
+            while (k <= j && k <= kFilterLookback) {
+                uint64_t jj = j - k;
+                if ((flags32[jj >> 5] >> (jj & 31)) & 1u) break;  // previous kept element reached
+                uint32_t x = lcp[jj];
+                v = x < v ? x : v;
+                k++;
+            }
+            if (k > kFilterLookback && k <= j) *overflow = 1;
+            uint32_t dst = woff[r * WARPS + warp] + __popc(masks[r] & lt_mask);
+            out_sa[dst] = sa[j];
+            out_lcp[dst] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) gather_u32_kernel(uint64_t m, const uint32_t* __restrict__ idx,
                                                             const uint32_t* __restrict__ src,
                                                             uint32_t* __restrict__ dst) {

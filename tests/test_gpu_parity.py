@@ -473,3 +473,19 @@ def test_cli_create_writes_golden_files(tmp_path, golden, fasta, flags):
     assert r.returncode == 0, r.stderr
     assert "Sorted" in r.stdout
     assert out.read_bytes() == (GOLDEN / "expected" / golden).read_bytes()
+
+
+def test_filter_after_full_sort_fast_and_generic_paths(S, monkeypatch):
+    """Repetitive DNA with scattered N: the filtered attempt gives up, everything is sorted with prefix
+    doubling, and the non-indexed suffixes are dropped afterwards -- by the look-back kernel, and (forced)
+    by the generic segmented-min scan.  A long N run overflows the look-back and takes the scan by itself."""
+    rng = random.Random(37)
+    base = dna_with_rare(rng, 60000, rare=b"N", rare_p=0.01, repeat_p=0.0)
+    text = base + base[:30000] + base[10000:50000] + b"$"      # long exact repeats => doubling
+    _, _, doubling = gpu_vs_oracle(S, text, is_dna=True)
+    assert doubling > 0
+    monkeypatch.setenv("SUFR_B200_DEBUG_SLOW_FILTER", "1")
+    gpu_vs_oracle(S, text, is_dna=True)
+    monkeypatch.delenv("SUFR_B200_DEBUG_SLOW_FILTER")
+    text2 = base[:20000] + b"N" * 3000 + base[:20000] + b"N" * 700 + base[5000:15000] + b"$"
+    gpu_vs_oracle(S, text2, is_dna=True)
