@@ -699,37 +699,32 @@ void Build::n_run_rule() {
 
 void Build::apply_filter() {
     if (!filter_active || s == 0) return;
-    // fast path: flags + ordered block compaction + short look-back for the LCP minimum
-    {
+    if (!getenv("SUFR_B200_DEBUG_SLOW_FILTER")) {
         const uint64_t per_block = (uint64_t)kBlock * kFilterRows;
         const uint32_t nblocks = div_up_u32(s, per_block);
         auto flags = dalloc<uint32_t>((size_t)nblocks * per_block / 32 + 1);
         auto counts = dalloc<uint32_t>(nblocks);
+        auto tail_min = dalloc<uint32_t>(nblocks);
         auto offsets = dalloc<uint32_t>(nblocks);
-        filter_flags_kernel<<<nblocks, kBlock, 0, st()>>>(d_text.get(), d_sa.get(), s, flags.get(), counts.get());
+        filter_flags_kernel<<<nblocks, kBlock, 0, st()>>>(d_text.get(), d_sa.get(), d_lcp.get(), s, flags.get(),
+                                                         counts.get(), tail_min.get());
         SUFR_KERNEL_CHECK();
         launched();
         uint32_t kept = scan_total(nblocks, BlockCountIn{counts.get()}, scan::SumU32{}, BlockOffsetOut{offsets.get()});
         if (kept == s) return;
         auto sa2 = dalloc<uint32_t>(kept);
         auto lcp2 = dalloc<uint32_t>(kept);
-        auto d_over = dalloc<uint32_t>(1);
-        SUFR_CUDA_CHECK(cudaMemsetAsync(d_over.get(), 0, 4, st()));
         filter_compact_kernel<<<nblocks, kBlock, 0, st()>>>(d_sa.get(), d_lcp.get(), s, flags.get(), offsets.get(),
-                                                           sa2.get(), lcp2.get(), d_over.get());
+                                                           counts.get(), tail_min.get(), sa2.get(), lcp2.get());
         SUFR_KERNEL_CHECK();
         launched();
-        uint32_t over = 0;
-        SUFR_CUDA_CHECK(cudaMemcpyAsync(&over, d_over.get(), 4, cudaMemcpyDeviceToHost, st()));
         SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
-        if (!over && !getenv("SUFR_B200_DEBUG_SLOW_FILTER")) {
-            d_sa = std::move(sa2);
-            d_lcp = std::move(lcp2);
-            s = kept;
-            return;
-        }
+        d_sa = std::move(sa2);
+        d_lcp = std::move(lcp2);
+        s = kept;
+        return;
     }
-    // generic path (long runs of dropped suffixes, e.g. N runs): segmented-min scan
+    // reference implementation of the same filter by segmented-min scans (debug knob above)
     FilterCountIn cin{d_text.get(), d_sa.get()};
     uint32_t kept = scan_total(s, cin, scan::SumU32{}, CountOnly{});
     if (kept == s) return;

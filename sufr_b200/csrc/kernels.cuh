@@ -811,16 +811,21 @@ struct FilterLcpOut {
         scanned[j] = ord_to_lcp((uint32_t)incl);
     }
 };
-// Fast suffix filter for the common case of few, scattered non-indexed suffixes: flags by ballot, ordered
-// block-level compaction, LCP of a kept element = min over the (short) run of dropped elements before it.
-// A run longer than kFilterLookback sets `overflow` and the generic segmented-min scan takes over.
+// Suffix filter after a full sort: flags by ballot, ordered block-level compaction, and the LCP of a kept
+// element = min over the run of dropped elements before it.  Dropped suffixes cluster by first symbol (all
+// N-starts are adjacent), so runs are few but can be millions long: a kept element looks back inside its
+// block, and past the block start it walks per-block summaries (min over a block's trailing dropped run).
 constexpr int kFilterRows = 8;
-constexpr uint32_t kFilterLookback = 256;
 __global__ void __launch_bounds__(kBlock) filter_flags_kernel(const uint8_t* __restrict__ text,
-                                                              const uint32_t* __restrict__ sa, uint64_t s,
+                                                              const uint32_t* __restrict__ sa,
+                                                              const uint32_t* __restrict__ lcp, uint64_t s,
                                                               uint32_t* __restrict__ flags32,
-                                                              uint32_t* __restrict__ block_counts) {
-    __shared__ uint32_t wsum[kBlock / 32];
+                                                              uint32_t* __restrict__ block_counts,
+                                                              uint32_t* __restrict__ block_tail_min) {
+    constexpr int WARPS = kBlock / 32;
+    __shared__ uint32_t wsum[WARPS];
+    __shared__ uint32_t wmask[kFilterRows * WARPS];
+    __shared__ uint32_t wmin[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t base = (uint64_t)blockIdx.x * kBlock * kFilterRows;
     uint32_t cnt = 0;
@@ -831,15 +836,40 @@ __global__ void __launch_bounds__(kBlock) filter_flags_kernel(const uint8_t* __r
         unsigned m = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) {
             flags32[(base + (uint64_t)r * kBlock) / 32 + warp] = m;
+            wmask[r * WARPS + warp] = m;
             cnt += __popc(m);
         }
     }
     if (lane == 0) wsum[warp] = cnt;
     __syncthreads();
+    // index (within the block) of the last kept element, -1 if none
+    int last_kept = -1;
+    for (int i = kFilterRows * WARPS - 1; i >= 0; i--) {
+        uint32_t m = wmask[i];
+        if (m) { last_kept = i * 32 + 31 - __clz((int)m); break; }
+    }
+    uint32_t tmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int r = 0; r < kFilterRows; r++) {
+        int local = r * kBlock + threadIdx.x;
+        uint64_t j = base + (uint64_t)local;
+        if (local > last_kept && j < s) {
+            uint32_t v = lcp[j];
+            tmin = v < tmin ? v : tmin;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        uint32_t o = __shfl_down_sync(0xffffffffu, tmin, off);
+        tmin = o < tmin ? o : tmin;
+    }
+    if (lane == 0) wmin[warp] = tmin;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kBlock / 32; w++) t += wsum[w];
+        uint32_t t = 0, mn = 0xFFFFFFFFu;
+        for (int w = 0; w < WARPS; w++) { t += wsum[w]; mn = wmin[w] < mn ? wmin[w] : mn; }
         block_counts[blockIdx.x] = t;
+        block_tail_min[blockIdx.x] = mn;
     }
 }
 struct BlockCountIn {
@@ -854,9 +884,10 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(const uint32_t* 
                                                                 const uint32_t* __restrict__ lcp, uint64_t s,
                                                                 const uint32_t* __restrict__ flags32,
                                                                 const uint32_t* __restrict__ block_offsets,
+                                                                const uint32_t* __restrict__ block_counts,
+                                                                const uint32_t* __restrict__ block_tail_min,
                                                                 uint32_t* __restrict__ out_sa,
-                                                                uint32_t* __restrict__ out_lcp,
-                                                                uint32_t* __restrict__ overflow) {
+                                                                uint32_t* __restrict__ out_lcp) {
     constexpr int WARPS = kBlock / 32;
     __shared__ uint32_t woff[kFilterRows * WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -884,15 +915,21 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(const uint32_t* 
         if (masks[r] & (1u << lane)) {
             uint64_t j = base + (uint64_t)r * kBlock + threadIdx.x;
             uint32_t v = lcp[j];
-            uint32_t k = 1;
-            while (k <= j && k <= kFilterLookback) {
-                uint64_t jj = j - k;
-                if ((flags32[jj >> 5] >> (jj & 31)) & 1u) break;  // previous kept element reached
+            uint64_t jj = j;
+            bool found = false;
+            while (jj > base) {  // dropped elements before j inside this block
+                jj--;
+                if ((flags32[jj >> 5] >> (jj & 31)) & 1u) { found = true; break; }
                 uint32_t x = lcp[jj];
                 v = x < v ? x : v;
-                k++;
             }
-            if (k > kFilterLookback && k <= j) *overflow = 1;
+            if (!found) {  // reached the block start: walk the summaries of the blocks before
+                for (long long b = (long long)blockIdx.x - 1; b >= 0; b--) {
+                    uint32_t x = block_tail_min[b];
+                    v = x < v ? x : v;
+                    if (block_counts[b]) break;  // that block holds a kept element: its trailing run ends the walk
+                }
+            }
             uint32_t dst = woff[r * WARPS + warp] + __popc(masks[r] & lt_mask);
             out_sa[dst] = sa[j];
             out_lcp[dst] = v;
