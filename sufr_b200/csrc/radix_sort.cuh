@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
             uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
             bool valid = idx < count;
             uint32_t d = digit_of(key[i], shift, dmask);
-            unsigned vm = __ballot_sync(0xffffffffu, valid);
+            // valid lanes of this row, computed instead of voted (votes are the bottleneck of this kernel)
+            int rem = (int)count - (int)(warp * (32 * IPT) + i * 32);
+            unsigned vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
             uint32_t r = 0;
             if (valid) {
                 // lanes holding the same digit, by one vote per digit bit (match.any saturates the ADU pipe:
