@@ -592,28 +592,52 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         refine_rounds++;
         final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
         auto keys = dalloc<uint64_t>(m);
-        auto segpos = dalloc<uint64_t>(m);
-        active_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, pos.get(),
-                                                               seg.get(), keys.get(), segpos.get());
-        SUFR_KERNEL_CHECK();
-        launched();
-        {   // stable sort by (segment, key word): LSD, key word first, then the segment bits
-            auto keys_b = dalloc<uint64_t>(m);
-            auto segpos_b = dalloc<uint64_t>(m);
-            bool in_b = rsort::sort_pairs<uint64_t, uint64_t>(keys.get(), keys_b.get(), segpos.get(), segpos_b.get(), m,
-                                                              64 - used, 64, d_counts.get(), st(), &ctx.launches);
-            if (in_b) { std::swap(keys, keys_b); std::swap(segpos, segpos_b); }
-            if (nseg > 1) {
-                int sb = bits_for(nseg - 1);
-                in_b = rsort::sort_pairs<uint64_t, uint64_t>(segpos.get(), segpos_b.get(), keys.get(), keys_b.get(), m, 32,
-                                                             32 + sb, d_counts.get(), st(), &ctx.launches);
-                if (in_b) { std::swap(keys, keys_b); std::swap(segpos, segpos_b); }
+        {
+            // small groups: sorted in registers by the thread at the group start
+            auto is_large = dalloc<uint8_t>(nseg ? nseg : 1);
+            auto d_large = dalloc<unsigned long long>(1);
+            SUFR_CUDA_CHECK(cudaMemsetAsync(is_large.get(), 0, nseg ? nseg : 1, st()));
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_large.get(), 0, 8, st()));
+            small_segments_kernel<<<grid_for(m, 1), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, seg.get(),
+                                                                      slot.get(), pos.get(), keys.get(), d_sa.get(),
+                                                                      is_large.get(), d_large.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+            unsigned long long any_large = 0;
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(&any_large, d_large.get(), 8, cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            if (any_large) {
+                // large groups: stable sort by (group, key word): LSD, key word first, then the group bits
+                auto idx = dalloc<uint32_t>(m);
+                auto lpos = dalloc<uint32_t>(m);
+                auto lseg = dalloc<uint32_t>(m);
+                unsigned long long lt = scan_total(m, LargeIn{seg.get(), is_large.get()}, scan::SumU64{},
+                                                   LargeOut{pos.get(), idx.get(), lpos.get(), lseg.get()});
+                const uint64_t ml = (uint32_t)lt;
+                const uint64_t nlseg = lt >> 32;
+                auto lkeys = dalloc<uint64_t>(ml);
+                auto segpos = dalloc<uint64_t>(ml);
+                active_keys_kernel<<<grid_for(ml, 2), kBlock, 0, st()>>>(ks, ml, (uint32_t)word, sentinel_ ? 1 : 0,
+                                                                        lpos.get(), lseg.get(), lkeys.get(), segpos.get());
+                SUFR_KERNEL_CHECK();
+                launched();
+                auto keys_b = dalloc<uint64_t>(ml);
+                auto segpos_b = dalloc<uint64_t>(ml);
+                bool in_b = rsort::sort_pairs<uint64_t, uint64_t>(lkeys.get(), keys_b.get(), segpos.get(), segpos_b.get(), ml,
+                                                                  64 - used, 64, d_counts.get(), st(), &ctx.launches);
+                if (in_b) { std::swap(lkeys, keys_b); std::swap(segpos, segpos_b); }
+                if (nlseg > 1) {
+                    int sb = bits_for(nlseg - 1);
+                    in_b = rsort::sort_pairs<uint64_t, uint64_t>(segpos.get(), segpos_b.get(), lkeys.get(), keys_b.get(), ml,
+                                                                 32, 32 + sb, d_counts.get(), st(), &ctx.launches);
+                    if (in_b) { std::swap(lkeys, keys_b); std::swap(segpos, segpos_b); }
+                }
+                scatter_large_kernel<<<grid_for(ml, 2), kBlock, 0, st()>>>(ml, lkeys.get(), segpos.get(), idx.get(),
+                                                                          slot.get(), keys.get(), pos.get(), d_sa.get());
+                SUFR_KERNEL_CHECK();
+                launched();
             }
         }
-        writeback_segpos_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, segpos.get(), slot.get(), pos.get(), d_sa.get());
-        SUFR_KERNEL_CHECK();
-        launched();
-        segpos.reset();
         ViewActive va{keys.get(), pos.get(), seg.get(), slot.get()};
         resolve_kernel<ViewActive><<<grid_for(m, 2), kBlock, 0, st()>>>(va, m, ks, (uint32_t)word, final_word, 0,
                                                                        d_lcp.get());

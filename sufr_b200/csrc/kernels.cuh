@@ -532,6 +532,95 @@ __global__ void __launch_bounds__(kBlock) active_keys_kernel(KeySpec ks, uint64_
     }
 }
 
+// Refinement of SMALL groups without a global sort.  On repetitive texts most unresolved groups are pairs
+// (a segment and its copy); the thread at the start of a group of at most kSmallSeg elements loads their
+// next key words, rank-sorts them in registers (stable) and writes keys, positions and SA slots in place.
+// Larger groups are flagged and go through the segmented radix sort.
+constexpr int kSmallSeg = 8;
+__global__ void __launch_bounds__(kBlock) small_segments_kernel(KeySpec ks, uint64_t m, uint32_t word, int filter,
+                                                                const uint32_t* __restrict__ seg,
+                                                                const uint32_t* __restrict__ slot,
+                                                                uint32_t* __restrict__ pos, uint64_t* __restrict__ keys,
+                                                                uint32_t* __restrict__ sa, uint8_t* __restrict__ is_large,
+                                                                unsigned long long* __restrict__ large_elems) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
+        const uint32_t g = seg[a];
+        if (a > 0 && seg[a - 1] == g) continue;  // not the first element of its group
+        int len = 1;
+        while (len <= kSmallSeg && a + len < m && seg[a + len] == g) len++;
+        if (len > kSmallSeg) {
+            is_large[g] = 1;
+            *large_elems = 1;  // "some group is large" (benign race: every writer stores 1)
+            continue;
+        }
+        uint32_t p[kSmallSeg];
+        uint64_t k[kSmallSeg];
+#pragma unroll
+        for (int i = 0; i < kSmallSeg; i++) {
+            if (i < len) {
+                p[i] = pos[a + i];
+                k[i] = (filter && !indexed_byte(ks.text[p[i]])) ? ~0ull : key_word(ks, p[i], word);
+            } else {
+                p[i] = 0;
+                k[i] = ~0ull;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSmallSeg; i++) {
+            if (i < len) {
+                int r = 0;
+#pragma unroll
+                for (int j = 0; j < kSmallSeg; j++)
+                    if (j < len && (k[j] < k[i] || (k[j] == k[i] && j < i))) r++;
+                keys[a + r] = k[i];
+                pos[a + r] = p[i];
+                sa[slot[a + r]] = p[i];
+            }
+        }
+    }
+}
+// elements of the large groups, in order
+struct LargeIn {
+    const uint32_t* seg;
+    const uint8_t* is_large;
+    __device__ unsigned long long operator()(uint64_t a) const {
+        uint32_t g = seg[a];
+        if (!is_large[g]) return 0ull;
+        bool head = a == 0 || seg[a - 1] != g;
+        return 1ull | ((unsigned long long)head << 32);
+    }
+};
+struct LargeOut {
+    const uint32_t* pos;
+    uint32_t* idx;      // index in the active arrays
+    uint32_t* lpos;
+    uint32_t* lseg;
+    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            uint32_t b = (uint32_t)incl - 1;
+            idx[b] = (uint32_t)a;
+            lpos[b] = pos[a];
+            lseg[b] = (uint32_t)(incl >> 32) - 1;
+        }
+    }
+};
+__global__ void __launch_bounds__(kBlock) scatter_large_kernel(uint64_t ml, const uint64_t* __restrict__ lkeys,
+                                                               const uint64_t* __restrict__ lsegpos,
+                                                               const uint32_t* __restrict__ idx,
+                                                               const uint32_t* __restrict__ slot,
+                                                               uint64_t* __restrict__ keys, uint32_t* __restrict__ pos,
+                                                               uint32_t* __restrict__ sa) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < ml; b += stride) {
+        uint32_t a = idx[b];
+        uint32_t p = (uint32_t)lsegpos[b];
+        keys[a] = lkeys[b];
+        pos[a] = p;
+        sa[slot[a]] = p;
+    }
+}
+
 // After the segmented sort: positions go back to their SA slots (the set of slots of a segment is unchanged).
 __global__ void __launch_bounds__(kBlock) writeback_segpos_kernel(uint64_t m, const uint64_t* __restrict__ segpos,
                                                                   const uint32_t* __restrict__ slot,
