@@ -186,6 +186,24 @@ class Build {
         return total;
     }
 
+    // two-step scan: pass 1 (reduce + spine) returns the grand total, pass 2 runs the output functor
+    template <typename Op, typename In>
+    typename Op::T scan_begin(uint64_t count, In in, Op op, DevBuf<typename Op::T>& partials) {
+        partials = dalloc<typename Op::T>(scan::partials_count(count));
+        scan::scan_reduce(count, in, op, partials.get(), st());
+        launched(count ? 2 : 0);
+        typename Op::T total;
+        size_t idx = count ? (size_t)div_up(count, scan::CHUNK) : 0;
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&total, partials.get() + idx, sizeof(total), cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        return total;
+    }
+    template <typename Op, typename In, typename Out>
+    void scan_finish(uint64_t count, In in, Op op, Out out, DevBuf<typename Op::T>& partials) {
+        scan::scan_apply(count, in, op, out, partials.get(), st());
+        launched(count ? 1 : 0);
+    }
+
     void encode(const uint8_t* d_raw);
     void find_n_runs();
     void make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bool sharded);
@@ -558,14 +576,15 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             // dense (repetitive text): order-preserving compaction by scan
             act_slot.reset();
             act_pos.reset();
-            unsigned long long tot = scan_total(r0n, ActiveIn<ViewAll>{v0, r0n, 0, sentinel_ ? 1 : 0}, scan::SumU64{}, CountOnlyU64{});
+            DevBuf<unsigned long long> part;
+            ActiveIn<ViewAll> ain{v0, r0n, 0, sentinel_ ? 1 : 0};
+            unsigned long long tot = scan_begin(r0n, ain, scan::SumU64{}, part);
             m = (uint32_t)tot;
             nseg = tot >> 32;
             slot = dalloc<uint32_t>(m);
             pos = dalloc<uint32_t>(m);
             seg = dalloc<uint32_t>(m);
-            scan_total(r0n, ActiveIn<ViewAll>{v0, r0n, 0, sentinel_ ? 1 : 0}, scan::SumU64{},
-                       ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()});
+            scan_finish(r0n, ain, scan::SumU64{}, ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()}, part);
         }
     }
     keys_sorted.reset();
@@ -644,14 +663,15 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         SUFR_KERNEL_CHECK();
         launched();
         if (final_word) return;
-        tot = scan_total(m, ActiveIn<ViewActive>{va, m, 0, sentinel_ ? 1 : 0}, scan::SumU64{}, CountOnlyU64{});
+        DevBuf<unsigned long long> part;
+        ActiveIn<ViewActive> ain{va, m, 0, sentinel_ ? 1 : 0};
+        tot = scan_begin(m, ain, scan::SumU64{}, part);
         uint64_t m2 = (uint32_t)tot, nseg2 = tot >> 32;
         if (m2 == 0) return;
         auto slot2 = dalloc<uint32_t>(m2);
         auto pos2 = dalloc<uint32_t>(m2);
         auto seg2 = dalloc<uint32_t>(m2);
-        scan_total(m, ActiveIn<ViewActive>{va, m, 0, sentinel_ ? 1 : 0}, scan::SumU64{},
-                   ActiveOut<ViewActive>{va, slot2.get(), pos2.get(), seg2.get()});
+        scan_finish(m, ain, scan::SumU64{}, ActiveOut<ViewActive>{va, slot2.get(), pos2.get(), seg2.get()}, part);
         slot = std::move(slot2);
         pos = std::move(pos2);
         seg = std::move(seg2);
@@ -685,14 +705,16 @@ void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint3
         uint32_t mark = kLcpLowerBound | (uint32_t)(h < 0x7FFFFFFFull ? h : 0x7FFFFFFFull);
         scan_total(m, DoublingStartIn{ck.get()}, scan::MaxU32{},
                    DoublingRankOut{ck.get(), slot.get(), pos.get(), isa_ptr, d_lcp.get(), mark});
-        unsigned long long tot = scan_total(m, DoublingActiveIn{ck.get(), m}, scan::SumU64{}, CountOnlyU64{});
+        DevBuf<unsigned long long> part;
+        DoublingActiveIn din{ck.get(), m};
+        unsigned long long tot = scan_begin(m, din, scan::SumU64{}, part);
         uint64_t m2 = (uint32_t)tot, nseg2 = tot >> 32;
         if (m2 == 0) break;
         auto slot2 = dalloc<uint32_t>(m2);
         auto pos2 = dalloc<uint32_t>(m2);
         auto seg2 = dalloc<uint32_t>(m2);
-        scan_total(m, DoublingActiveIn{ck.get(), m}, scan::SumU64{},
-                   DoublingActiveOut{slot.get(), pos.get(), slot2.get(), pos2.get(), seg2.get()});
+        scan_finish(m, din, scan::SumU64{}, DoublingActiveOut{slot.get(), pos.get(), slot2.get(), pos2.get(), seg2.get()},
+                    part);
         slot = std::move(slot2);
         pos = std::move(pos2);
         seg = std::move(seg2);

@@ -74,21 +74,22 @@ __device__ __forceinline__ typename Op::T block_inclusive(typename Op::T v, Op o
     return incl;
 }
 
+// Each thread owns ITEMS consecutive elements (thread-local sequential scan), so a chunk needs ONE
+// block-level scan instead of one per row of 256 elements.
 template <typename Op, typename In>
 __global__ void __launch_bounds__(BLOCK) reduce_kernel(uint64_t n, In in, Op op, typename Op::T* partials) {
     using T = typename Op::T;
     __shared__ T smem[BLOCK / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * CHUNK;
-    T carry = Op::identity();
+    const uint64_t i0 = (uint64_t)blockIdx.x * CHUNK + (uint64_t)threadIdx.x * ITEMS;
+    T acc = Op::identity();
+#pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        uint64_t i = base + (uint64_t)k * BLOCK + threadIdx.x;
-        T v = i < n ? in(i) : Op::identity();
-        T total;
-        block_inclusive(v, op, smem, total);
-        carry = op(carry, total);
-        if (base + (uint64_t)(k + 1) * BLOCK >= n) break;
+        uint64_t i = i0 + k;
+        if (i < n) acc = op(acc, in(i));
     }
-    if (threadIdx.x == 0) partials[blockIdx.x] = carry;
+    T total;
+    block_inclusive(acc, op, smem, total);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
 }
 
 // Single block: exclusive scan of the per-chunk partials, in place. `total_out` receives the grand total.
@@ -125,21 +126,57 @@ __global__ void __launch_bounds__(BLOCK) apply_kernel(uint64_t n, In in, Op op, 
                                                       Out out) {
     using T = typename Op::T;
     __shared__ T smem[BLOCK / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * CHUNK;
-    T carry = partials[blockIdx.x];
+    const uint64_t i0 = (uint64_t)blockIdx.x * CHUNK + (uint64_t)threadIdx.x * ITEMS;
+    T v[ITEMS];
+    T acc = Op::identity();
+#pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        uint64_t i = base + (uint64_t)k * BLOCK + threadIdx.x;
-        T v = i < n ? in(i) : Op::identity();
-        T total;
-        T incl = block_inclusive(v, op, smem, total);
-        incl = op(carry, incl);
-        if (i < n) out(i, v, incl);
-        carry = op(carry, total);
-        if (base + (uint64_t)(k + 1) * BLOCK >= n) break;
+        uint64_t i = i0 + k;
+        v[k] = i < n ? in(i) : Op::identity();
+        acc = op(acc, v[k]);
+    }
+    T total;
+    T incl = block_inclusive(acc, op, smem, total);
+    // exclusive prefix of this thread = carry (+) inclusive of the previous thread
+    T prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    __shared__ T last_of_warp[BLOCK / 32];
+    if ((threadIdx.x & 31) == 31) last_of_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    T prefix = partials[blockIdx.x];
+    if (threadIdx.x != 0) prefix = op(prefix, (threadIdx.x & 31) == 0 ? last_of_warp[(threadIdx.x >> 5) - 1] : prev);
+    T run = prefix;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        uint64_t i = i0 + k;
+        run = op(run, v[k]);
+        if (i < n) out(i, v[k], run);
     }
 }
 
 inline size_t partials_count(uint64_t n) { return (size_t)div_up(n, CHUNK) + 1; }
+
+// Two-step form: scan_reduce leaves the exclusive chunk prefixes in `partials` (and the grand total in its last
+// element) so that the caller can size its outputs before scan_apply runs the second pass.
+template <typename Op, typename In>
+void scan_reduce(uint64_t n, In in, Op op, typename Op::T* partials, cudaStream_t stream) {
+    if (n == 0) {
+        typename Op::T id = Op::identity();
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(partials, &id, sizeof(id), cudaMemcpyHostToDevice, stream));
+        return;
+    }
+    uint32_t nblocks = div_up_u32(n, CHUNK);
+    reduce_kernel<Op, In><<<nblocks, BLOCK, 0, stream>>>(n, in, op, partials);
+    SUFR_KERNEL_CHECK();
+    spine_kernel<Op><<<1, BLOCK, 0, stream>>>(nblocks, op, partials, partials + nblocks);
+    SUFR_KERNEL_CHECK();
+}
+template <typename Op, typename In, typename Out>
+void scan_apply(uint64_t n, In in, Op op, Out out, const typename Op::T* partials, cudaStream_t stream) {
+    if (n == 0) return;
+    uint32_t nblocks = div_up_u32(n, CHUNK);
+    apply_kernel<Op, In, Out><<<nblocks, BLOCK, 0, stream>>>(n, in, op, partials, out);
+    SUFR_KERNEL_CHECK();
+}
 
 // `partials` must hold partials_count(n) elements; the last one receives the grand total.
 template <typename Op, typename In, typename Out>
