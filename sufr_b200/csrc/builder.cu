@@ -204,6 +204,7 @@ class Build {
         launched(count ? 1 : 0);
     }
 
+    bool looks_repetitive();
     void encode(const uint8_t* d_raw);
     void find_n_runs();
     void make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bool sharded);
@@ -311,6 +312,36 @@ void Build::encode(const uint8_t* d_raw) {
         }
     }
     SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));  // lut / present are freed on return
+}
+
+// Cheap probe (4 M sampled keys, one small sort): does the text have so many long repeats that the build will
+// need prefix doubling?  Decides whether the suffix filter is applied before the sort (cheap, but a text that
+// then needs doubling has to be redone over all positions) or after it.
+bool Build::looks_repetitive() {
+    if (ks.mode != kModeFull || n < (1u << 24)) return false;
+    const uint64_t count = 1u << 22;
+    const uint64_t stride_pos = n / count;
+    auto keys = dalloc<uint64_t>(count), keys_b = dalloc<uint64_t>(count);
+    auto pos = dalloc<uint32_t>(count), pos_b = dalloc<uint32_t>(count);
+    auto counts = dalloc<uint32_t>(rsort::counts_words());
+    auto d_eq = dalloc<unsigned long long>(1);
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_eq.get(), 0, 8, st()));
+    sample_keys_kernel<<<grid_for(count, 2), kBlock, 0, st()>>>(ks, stride_pos, count, keys.get(), pos.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+    const int used = (int)(ks.pt.K * ks.pt.bits);
+    const int begin_bit = ks.fast2 ? 64 - kFast2SortBits : 64 - used;
+    bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys.get(), keys_b.get(), pos.get(), pos_b.get(), count, begin_bit, 64,
+                                                      counts.get(), st(), &ctx.launches);
+    count_equal_neighbours_kernel<<<grid_for(count, 4), kBlock, 0, st()>>>(in_b ? keys_b.get() : keys.get(), count,
+                                                                          ks.fast2 ? kFast2CmpMask : ~0ull, d_eq.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+    unsigned long long eq = 0;
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(&eq, d_eq.get(), 8, cudaMemcpyDeviceToHost, st()));
+    SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+    // a random text gives count^2 / (2 * 4^20) ~ 8 equal neighbours among 4 M samples of 20 symbols
+    return eq > 512;
 }
 
 void Build::find_n_runs() {
@@ -871,6 +902,7 @@ void Build::run(SufrB200Result* out) {
     // repeats deeper than the word-refinement limit need the ranks of ALL positions: redo unfiltered and
     // unsharded, filter afterwards, and cut this rank's slice out of the global result.
     bool prefilter = filter_active, sharded = args.world_size > 1, sliced = false;
+    if (prefilter && !sharded && !getenv("SUFR_B200_DEBUG_NO_PROBE") && looks_repetitive()) prefilter = false;
     try {
         sort_phase(prefilter, sharded);
     } catch (const NeedFullSort&) {

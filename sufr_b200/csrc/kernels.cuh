@@ -150,6 +150,28 @@ __global__ void __launch_bounds__(kBlock) keygen_fast2_kernel(KeySpec ks, uint64
     }
 }
 
+// Repetitiveness probe: first keys of every `stride`-th position; after sorting them, the number of adjacent
+// equal keys tells a random-like text (a handful) from one with long repeats (thousands).
+__global__ void __launch_bounds__(kBlock) sample_keys_kernel(KeySpec ks, uint64_t stride_pos, uint64_t count,
+                                                             uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t p = i * stride_pos;
+        keys[i] = first_key(ks, p);
+        pos[i] = (uint32_t)p;
+    }
+}
+__global__ void __launch_bounds__(kBlock) count_equal_neighbours_kernel(const uint64_t* __restrict__ keys, uint64_t count,
+                                                                        uint64_t mask, unsigned long long* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long c = 0;
+    for (uint64_t i = 1 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        c += (((keys[i] ^ keys[i - 1]) & mask) == 0) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // Number of indexed suffixes (16 bytes per load).
 __global__ void __launch_bounds__(kBlock) count_indexed_kernel(const uint8_t* __restrict__ text, uint64_t n,
                                                                unsigned long long* __restrict__ out) {
@@ -346,6 +368,36 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(View v, uint64_t m, Key
     }
 }
 
+// Unordered append of the flagged elements of a 256-element block row: ballots per warp, one global atomic
+// per row (a per-warp atomic on a single counter serialises when most warps have something to append).
+__device__ __forceinline__ void block_append(bool active, uint32_t slot_val, uint32_t pos_val,
+                                             uint32_t* __restrict__ act_slot, uint32_t* __restrict__ act_pos,
+                                             unsigned long long* __restrict__ act_count, uint64_t capacity,
+                                             uint32_t* wcount, unsigned long long* gbase) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int w = 0; w < kBlock / 32; w++) {
+            uint32_t t = wcount[w];
+            wcount[w] = acc;
+            acc += t;
+        }
+        *gbase = acc ? atomicAdd(act_count, (unsigned long long)acc) : 0ull;
+    }
+    __syncthreads();
+    if (active) {
+        unsigned long long idx = *gbase + wcount[warp] + __popc(m & ((1u << lane) - 1u));
+        if (idx < capacity) {
+            act_slot[idx] = slot_val;
+            act_pos[idx] = pos_val;
+        }
+    }
+    __syncthreads();
+}
+
 // Round 0 in one pass over the sorted keys: LCP of every boundary (as resolve_kernel) and, because the
 // unresolved elements are normally a tiny fraction, an UNORDERED warp-aggregated append of (slot, position)
 // of every element that is still in a group of size > 1.  The short list is then sorted by slot.
@@ -357,11 +409,11 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
                                                                  uint32_t* __restrict__ act_pos,
                                                                  unsigned long long* __restrict__ act_count,
                                                                  uint64_t capacity) {
+    __shared__ uint32_t wcount[kBlock / 32];
+    __shared__ unsigned long long gbase;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < s; j0 += stride) {
-        const uint64_t j = j0 + lane;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < s; base += stride) {
+        const uint64_t j = base + threadIdx.x;
         bool active = false;
         uint32_t p = 0;
         if (j < s) {
@@ -384,22 +436,10 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
             }
             if (!final_word) active = !head || (j + 1 < s && keys[j + 1] == kj);
         }
-        unsigned m = __ballot_sync(0xffffffffu, active);
-        if (m) {
-            int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(act_count, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (active) {
-                unsigned long long idx = base + __popc(m & lt_mask);
-                if (idx < capacity) {
-                    act_slot[idx] = (uint32_t)j;
-                    act_pos[idx] = p;
-                }
-            }
-        }
+        block_append(active, (uint32_t)j, p, act_slot, act_pos, act_count, capacity, wcount, &gbase);
     }
 }
+
 // Round 0 of the 2-bit fast path.  Only the top kFast2SortBits of the keys are sorted: a group is a run of
 // equal sorted bits, everything in a group of size > 1 is collected for the exact refinement (which starts
 // at key word 0).  Boundary LCP = clz(x ^ y) / 2 when neither key contains fill, else an exact comparison
@@ -412,17 +452,18 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
                                                                 uint32_t* __restrict__ act_pos,
                                                                 unsigned long long* __restrict__ act_count,
                                                                 uint64_t capacity) {
+    __shared__ uint32_t wcount[kBlock / 32];
+    __shared__ unsigned long long gbase;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < s; j0 += stride) {
-        const uint64_t j = j0 + lane;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < s; base += stride) {
+        const uint64_t j = base + threadIdx.x;
         bool active = false;
         uint32_t p = 0;
         if (j < s) {
             uint64_t kj = keys[j];
             p = pos[j];
             bool head = true;
+            bool next_same = j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0;
             if (j == 0) {
                 lcp[0] = 0;
             } else {
@@ -433,7 +474,6 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
                 } else {
                     // The LCP of a boundary can be read off the two keys only if neither contains fill and the
                     // final neighbours are already known, i.e. both adjacent groups are singletons.
-                    bool next_same = j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0;
                     bool prev_multi = j >= 2 && ((keys[j - 2] ^ kp) & kFast2CmpMask) == 0;
                     if (((kp | kj) & 1ull) == 0 && !next_same && !prev_multi)
                         lcp[j] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
@@ -441,22 +481,9 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
                         lcp[j] = kLcpFixup;
                 }
             }
-            active = !head || (j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0);
+            active = !head || next_same;
         }
-        unsigned m = __ballot_sync(0xffffffffu, active);
-        if (m) {
-            int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(act_count, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (active) {
-                unsigned long long idx = base + __popc(m & lt_mask);
-                if (idx < capacity) {
-                    act_slot[idx] = (uint32_t)j;
-                    act_pos[idx] = p;
-                }
-            }
-        }
+        block_append(active, (uint32_t)j, p, act_slot, act_pos, act_count, capacity, wcount, &gbase);
     }
 }
 
