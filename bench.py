@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", type=int, default=4000, help="sampled SA/LCP checks after the timed region")
+    ap.add_argument("--repetitive", action="store_true",
+                    help="also time the repetitive variant (config 2b, generated on the host: adds ~1 min)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
@@ -263,6 +265,11 @@ def main():
                "sample": f"first {sample_n} bytes of the workload text (u32 indices, -n {parts}); oracle "
                          f"restatement of sufr_builder.rs, {cores} threads, partitions in RAM; {dt:.2f} s"}
 
+    # ---------------- repetitive variant of the same workload (BASELINE: "random and repetitive FASTA"), N=1 only
+    variants = None
+    if args.repetitive and world == 1:
+        variants = {"repetitive": run_repetitive(args, S, ctx, dev)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -285,19 +292,55 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "rsort::downsweep_kernel<u64,u32> (main sort)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
-                         "traffic": None, "launch_ms": dk_ms, "launches_per_step": tm["dominant_kernel_launches"],
+                         "traffic": traffic_estimate(tm["dominant_kernel_bytes"]), "launch_ms": dk_ms, "launches_per_step": tm["dominant_kernel_launches"],
                          "share_of_step": tm["dominant_kernel_ms"] / (1e3 * elapsed / args.steps),
                          "job": {"algorithmic_bytes": job_bytes,
                                  "achieved": job_bytes * args.steps / elapsed / 1e9 / world,
                                  "frac": job_bytes * args.steps / elapsed / 1e9 / world / peak,
                                  "note": "A = n + 2*s*sizeof(T) per SURVEY 8(d), per GPU"}},
             "cpu_baseline": cpu,
+            "variants": variants,
             "phases_ms": {k: v for k, v in tm.items() if k.endswith("_ms")},
             "verify": verify,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def traffic_estimate(algorithmic_bytes):
+    """DRAM bytes per launch of the dominant kernel: the ratio measured by `ncu --set full` on the 200 Mbp
+    capture (profiles/r1_v3_downsweep_fast2_raw.csv: 2.794 GB read + 2.711 GB written for 4.800 GB
+    algorithmic) applied to this launch's algorithmic bytes."""
+    return {"bytes": algorithmic_bytes * (2.793825 + 2.711042) / 4.800000576, "ratio_to_algorithmic": 1.1468,
+            "source": "profiles/r1_v3_downsweep_fast2_raw.csv (200 Mbp capture, scaled by element count)"}
+
+
+def run_repetitive(args, S, ctx, dev):
+    """One warm-up + two timed device-resident builds of workloads.config2_repetitive at the same size."""
+    import torch
+    import workloads
+    sys.path.insert(0, str(ROOT / "tools"))
+    w = workloads.config2_repetitive(args.bases)
+    t = torch.frombuffer(bytearray(w.text), dtype=torch.uint8).to(dev)
+    bargs = S.SufrBuilderArgs(text=b"", is_dna=True, sequence_starts=w.sequence_starts, sequence_names=w.sequence_names)
+    times, last = [], None
+    for i in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = S.build(bargs, index_bits=args.index_bits, ctx=ctx, result_memory=S.MEM_DEVICE,
+                    device_text=(t.data_ptr(), t.numel()))
+        torch.cuda.synchronize()
+        if i:
+            times.append(time.perf_counter() - t0)
+        info = (r.num_suffixes, int(r.c.refine_rounds), int(r.c.doubling_rounds), r.timings)
+        v = verify_sample(r, t, 1000, 0, 2) if i == 2 else None
+        r.free()
+    ms = 1e3 * sum(times) / len(times)
+    return {"workload": "config 2b: ~50 % of the bases are mutated copies of earlier 0.3-6 kb segments, some N / "
+                        "soft-masked stretches", "ms_per_step": ms, "value": info[0] / (ms * 1e-3),
+            "unit": "suffixes/s", "refine_rounds": info[1], "doubling_rounds": info[2],
+            "phases_ms": {k: v for k, v in info[3].items() if k.endswith("_ms")}, "verify": v}
 
 
 def verify_sample(res, d_text, k, rank, world):
