@@ -158,6 +158,7 @@ class Build {
     DevBuf<uint8_t> d_cls;
     bool sentinel_ = false;             // filtered suffixes ride through the sort with key ~0
     uint64_t sort_n_ = 0;               // elements handed to the main sort (>= s when sentinel_)
+    uint64_t indexed_count_ = 0;        // bytes in ACGT$ (counted by the transform kernel)
     DevBuf<uint64_t> d_nstarts, d_nends;
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
@@ -226,20 +227,22 @@ static int bits_for(uint64_t v) {  // number of bits needed to represent values 
 void Build::encode(const uint8_t* d_raw) {
     d_text = dalloc<uint8_t>(n + 16);
     auto d_present = dalloc<uint32_t>(256);
-    auto d_sample = dalloc<unsigned long long>(256);
+    auto d_sample = dalloc<unsigned long long>(257);  // [256] = number of indexed suffix starts
     SUFR_CUDA_CHECK(cudaMemsetAsync(d_present.get(), 0, 256 * sizeof(uint32_t), st()));
-    SUFR_CUDA_CHECK(cudaMemsetAsync(d_sample.get(), 0, 256 * sizeof(unsigned long long), st()));
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_sample.get(), 0, 257 * sizeof(unsigned long long), st()));
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_text.get() + n, 0, 16, st()));
     if (n) {
         transform_kernel<<<grid_for(n, 16), kBlock, 0, st()>>>(d_raw, d_text.get(), n, args.ignore_softmask,
-                                                               d_present.get(), d_sample.get());
+                                                               d_present.get(), d_sample.get(), d_sample.get() + 256);
         SUFR_KERNEL_CHECK();
         launched();
     }
     uint32_t present[256];
-    unsigned long long sample[256];
+    unsigned long long sample[257];
     SUFR_CUDA_CHECK(cudaMemcpyAsync(present, d_present.get(), sizeof(present), cudaMemcpyDeviceToHost, st()));
     SUFR_CUDA_CHECK(cudaMemcpyAsync(sample, d_sample.get(), sizeof(sample), cudaMemcpyDeviceToHost, st()));
     SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+    indexed_count_ = sample[256];
     uint8_t lut[256];
     alphabet = 0;
     for (int b = 0; b < 256; b++) lut[b] = present[b] ? (uint8_t)(++alphabet) : 0;
@@ -442,17 +445,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     const int used_bits = (int)(ks.pt.K * ks.pt.bits);
     uint64_t kept = n;     // suffixes that survive the filter (all ranks' ranges together)
     uint64_t sort_n = n;   // elements handed to the sort
-    if (prefilter && n) {
-        auto d_cnt = dalloc<unsigned long long>(1);
-        SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
-        count_indexed_kernel<<<grid_for(n, 64), kBlock, 0, st()>>>(d_text.get(), n, d_cnt.get());
-        SUFR_KERNEL_CHECK();
-        launched();
-        unsigned long long c = 0;
-        SUFR_CUDA_CHECK(cudaMemcpyAsync(&c, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st()));
-        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
-        kept = c;
-    }
+    if (prefilter && n) kept = indexed_count_;
     // Few filtered suffixes (the common case: delimiters, sparse N): no compaction at all, they get the
     // key ~0 and drop off the end of the sorted array.  Needs an unused low bit in the packed word.
     const bool sentinel = prefilter && !sharded && used_bits < 64 && (n - kept) * 16 <= n;

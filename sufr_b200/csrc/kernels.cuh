@@ -28,11 +28,13 @@ inline uint32_t grid_for(uint64_t n, int per_thread = 1) {
 __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __restrict__ in,
                                                            uint8_t* __restrict__ out, uint64_t n,
                                                            int ignore_softmask, uint32_t* __restrict__ present,
-                                                           unsigned long long* __restrict__ sample_counts) {
+                                                           unsigned long long* __restrict__ sample_counts,
+                                                           unsigned long long* __restrict__ indexed_count) {
     __shared__ uint32_t seen[256];
     __shared__ uint32_t cnt[256];  // byte counts of a 1/64 sample (chooses the 4 "regular" bytes)
     seen[threadIdx.x] = 0;
     cnt[threadIdx.x] = 0;
+    unsigned long long nidx = 0;   // bytes that start an indexed suffix under --dna (sufr_builder.rs:446-449)
     __syncthreads();
     const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const uint64_t nvec = aligned ? n / 16 : 0;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
                 if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
                 seen[c] = 1;
                 if ((v & 63) == 0) atomicAdd(&cnt[c], 1u);
+                nidx += (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '$') ? 1 : 0;
                 r |= c << (8 * b);
             }
             w[k] = r;
@@ -59,8 +62,12 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
         uint32_t c = in[i];
         if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
         seen[c] = 1;
+        nidx += (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '$') ? 1 : 0;
         out[i] = (uint8_t)c;
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) nidx += __shfl_down_sync(0xffffffffu, nidx, off);
+    if ((threadIdx.x & 31) == 0 && nidx) atomicAdd(indexed_count, nidx);
     __syncthreads();
     if (seen[threadIdx.x]) present[threadIdx.x] = 1;
     if (cnt[threadIdx.x]) atomicAdd(&sample_counts[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
@@ -79,9 +86,20 @@ __global__ void __launch_bounds__(kBlock) pack2_kernel(const uint8_t* __restrict
         uint64_t base = w * 32;
         uint64_t x = 0;
         uint32_t m = 0;
+        uint32_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (base < n) {  // two 16-byte loads (the text buffer is 16-byte aligned and padded by 16 bytes)
+            uint4 a = *reinterpret_cast<const uint4*>(text + base);
+            bytes[0] = a.x; bytes[1] = a.y; bytes[2] = a.z; bytes[3] = a.w;
+            if (base + 16 < n) {
+                uint4 c4 = *reinterpret_cast<const uint4*>(text + base + 16);
+                bytes[4] = c4.x; bytes[5] = c4.y; bytes[6] = c4.z; bytes[7] = c4.w;
+            }
+        }
+#pragma unroll
         for (uint32_t j = 0; j < 32; j++) {
             uint64_t i = base + j;
-            uint32_t c = i < n ? lut[text[i]] : 4u;  // beyond the text: irregular, class 0
+            uint32_t byte = (bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            uint32_t c = i < n ? lut[byte] : 4u;  // beyond the text: irregular, class 0
             x |= (uint64_t)(c & 3u) << (62 - 2 * j);
             m |= (c >> 2) << (31 - j);
         }
@@ -91,23 +109,36 @@ __global__ void __launch_bounds__(kBlock) pack2_kernel(const uint8_t* __restrict
     }
 }
 
-// One 64-bit word (K symbols) per thread.
+// One 64-bit word (K symbols) per thread.  The block's 256*K text bytes are staged in shared memory with
+// 16-byte loads (the text buffer is padded by 16 bytes); `text` must be 16-byte aligned.
 __global__ void __launch_bounds__(kBlock) pack_kernel(const uint8_t* __restrict__ text, uint64_t n,
                                                       const uint8_t* __restrict__ code_lut, uint32_t bits,
                                                       uint32_t K, uint64_t num_words, uint64_t* __restrict__ words) {
     __shared__ uint8_t lut[256];
+    __shared__ __align__(16) uint8_t raw[kBlock * 64];
     lut[threadIdx.x] = code_lut[threadIdx.x];
-    __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < num_words; w += stride) {
-        uint64_t base = w * K;
-        uint64_t x = 0;
-        for (uint32_t j = 0; j < K; j++) {
-            uint64_t i = base + j;
-            uint64_t c = i < n ? lut[text[i]] : 0;
-            x |= c << (64 - bits * (j + 1));
+    const uint64_t blocks = (num_words + kBlock - 1) / kBlock;
+    for (uint64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+        const uint64_t byte0 = b * kBlock * K;
+        const uint32_t nvec = (kBlock * K + 15) / 16;
+        __syncthreads();
+        for (uint32_t v = threadIdx.x; v < nvec; v += kBlock) {
+            uint64_t off = byte0 + (uint64_t)v * 16;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (off < n) x = *reinterpret_cast<const uint4*>(text + off);  // may read the 16 padding bytes
+            reinterpret_cast<uint4*>(raw)[v] = x;
         }
-        words[w] = x;
+        __syncthreads();
+        const uint64_t w = b * kBlock + threadIdx.x;
+        if (w < num_words) {
+            const uint64_t base = w * K;
+            uint64_t x = 0;
+            for (uint32_t j = 0; j < K; j++) {
+                uint64_t c = base + j < n ? lut[raw[threadIdx.x * K + j]] : 0;
+                x |= c << (64 - bits * (j + 1));
+            }
+            words[w] = x;
+        }
     }
 }
 
