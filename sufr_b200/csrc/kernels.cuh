@@ -8,6 +8,23 @@ namespace sufr {
 
 constexpr int kBlock = 256;
 
+// Exclusive scan of 64 shared-memory counters by warp 0 (two per lane); returns the total in every lane of
+// warp 0.  Call from warp 0 only, between two __syncthreads().
+__device__ __forceinline__ uint32_t warp_scan64(uint32_t* cnt) {
+    const int lane = threadIdx.x & 31;
+    uint32_t v0 = cnt[2 * lane], v1 = cnt[2 * lane + 1];
+    uint32_t s = v0 + v1, incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    uint32_t excl = incl - s;
+    cnt[2 * lane] = excl;
+    cnt[2 * lane + 1] = excl + v0;
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
+
 // scan outputs that only want the grand total
 struct CountOnly {
     __device__ void operator()(uint64_t, uint32_t, uint32_t) const {}
@@ -304,14 +321,10 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
                 takes |= (take ? 1u : 0u) << r;
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t acc = 0;
-                for (int i = 0; i < kSelectRows * WARPS; i++) {
-                    uint32_t t = wcount[i];
-                    wcount[i] = acc;
-                    acc += t;
-                }
-                gbase = acc ? atomicAdd(count, (unsigned long long)acc) : 0ull;
+            if (warp == 0) {
+                static_assert(kSelectRows * WARPS == 64, "warp_scan64");
+                uint32_t acc = warp_scan64(wcount);
+                if (lane == 0) gbase = acc ? atomicAdd(count, (unsigned long long)acc) : 0ull;
             }
             __syncthreads();
 #pragma unroll
@@ -1048,15 +1061,12 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(const uint32_t* 
         if (lane == 0) woff[r * WARPS + warp] = __popc(masks[r]);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = block_offsets[blockIdx.x];
-        for (int i = 0; i < kFilterRows * WARPS; i++) {
-            uint32_t t = woff[i];
-            woff[i] = acc;
-            acc += t;
-        }
+    if (warp == 0) {
+        static_assert(kFilterRows * WARPS == 64, "warp_scan64");
+        warp_scan64(woff);
     }
     __syncthreads();
+    const uint32_t block_base = block_offsets[blockIdx.x];
 #pragma unroll
     for (int r = 0; r < kFilterRows; r++) {
         if (masks[r] & (1u << lane)) {
@@ -1077,7 +1087,7 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(const uint32_t* 
                     if (block_counts[b]) break;  // that block holds a kept element: its trailing run ends the walk
                 }
             }
-            uint32_t dst = woff[r * WARPS + warp] + __popc(masks[r] & lt_mask);
+            uint32_t dst = block_base + woff[r * WARPS + warp] + __popc(masks[r] & lt_mask);
             out_sa[dst] = sa[j];
             out_lcp[dst] = v;
         }
