@@ -292,7 +292,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "rsort::downsweep_kernel<u64,u32> (main sort)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
-                         "traffic": traffic_estimate(tm["dominant_kernel_bytes"]), "launch_ms": dk_ms, "launches_per_step": tm["dominant_kernel_launches"],
+                         "traffic": traffic_estimate(tm["dominant_kernel_bytes"]), "traffic_source": TRAFFIC_SOURCE,
+                         "algorithmic_bytes": tm["dominant_kernel_bytes"], "launch_ms": dk_ms, "launches_per_step": tm["dominant_kernel_launches"],
                          "share_of_step": tm["dominant_kernel_ms"] / (1e3 * elapsed / args.steps),
                          "job": {"algorithmic_bytes": job_bytes,
                                  "achieved": job_bytes * args.steps / elapsed / 1e9 / world,
@@ -308,12 +309,14 @@ def main():
         dist.destroy_process_group()
 
 
+TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on the "
+                  "200 Mbp workload (profiles/r1_v3_downsweep_fast2_raw.csv: 2.794 GB + 2.711 GB for 4.800 GB "
+                  "algorithmic), scaled to this launch's element count")
+
+
 def traffic_estimate(algorithmic_bytes):
-    """DRAM bytes per launch of the dominant kernel: the ratio measured by `ncu --set full` on the 200 Mbp
-    capture (profiles/r1_v3_downsweep_fast2_raw.csv: 2.794 GB read + 2.711 GB written for 4.800 GB
-    algorithmic) applied to this launch's algorithmic bytes."""
-    return {"bytes": algorithmic_bytes * (2.793825 + 2.711042) / 4.800000576, "ratio_to_algorithmic": 1.1468,
-            "source": "profiles/r1_v3_downsweep_fast2_raw.csv (200 Mbp capture, scaled by element count)"}
+    """DRAM bytes per launch of the dominant kernel (see TRAFFIC_SOURCE)."""
+    return algorithmic_bytes * (2.793825 + 2.711042) / 4.800000576
 
 
 def run_repetitive(args, S, ctx, dev):

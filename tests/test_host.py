@@ -222,7 +222,7 @@ GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
 import torch.distributed as dist
-from sufr_b200.distributed import gather_meta, previous_last_suffix, shard_layout
+from sufr_b200.distributed import finish_shard, gather_meta, previous_last_suffix, shard_layout
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 mine = [(4, 100, 101), (6, 200, 201)][rank]
@@ -231,6 +231,22 @@ assert meta == [(4, 100, 101), (6, 200, 201)], meta
 offs, total = shard_layout(meta)
 assert (offs, total) == ([0, 4], 10)
 assert previous_last_suffix(meta, rank) == (None if rank == 0 else 101)
+
+
+class FakeShard:  # what finish_shard needs from a BuildResult
+    def __init__(self, n, first, last):
+        self.num_suffixes, self.first_suffix, self.last_suffix = n, first, last
+        self.layout, self.seam = None, None
+    def set_shard_layout(self, off, tot):
+        self.layout = (off, tot)
+    def patch_seam(self, prev):
+        self.seam = prev
+
+
+shard = FakeShard(*mine)
+finish_shard(shard)
+assert shard.layout == ((0, 10) if rank == 0 else (4, 10)), shard.layout
+assert shard.seam == (None if rank == 0 else 101), shard.seam
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
