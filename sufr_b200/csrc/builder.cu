@@ -333,11 +333,11 @@ bool Build::looks_repetitive() {
     SUFR_KERNEL_CHECK();
     launched();
     const int used = (int)(ks.pt.K * ks.pt.bits);
-    const int begin_bit = ks.fast2 ? 64 - kFast2SortBits : 64 - used;
+    const int begin_bit = ks.fast2 ? 64 - kFast2ProbeBits : 64 - used;
     bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys.get(), keys_b.get(), pos.get(), pos_b.get(), count, begin_bit, 64,
                                                       counts.get(), st(), &ctx.launches);
     count_equal_neighbours_kernel<<<grid_for(count, 4), kBlock, 0, st()>>>(in_b ? keys_b.get() : keys.get(), count,
-                                                                          ks.fast2 ? kFast2CmpMask : ~0ull, d_eq.get());
+                                                                          ks.fast2 ? ~0ull << (64 - kFast2ProbeBits) : ~0ull, d_eq.get());
     SUFR_KERNEL_CHECK();
     launched();
     unsigned long long eq = 0;
@@ -550,8 +550,15 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // sorted a 2-bit approximation of the first symbols, so its refinement starts with word 0.
     int word = fast2 ? -1 : 0;
     int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
-    const uint64_t cmp_mask = fast2 ? kFast2CmpMask : ~0ull;
-    ViewAll v0{keys_sorted.get(), d_sa.get(), cmp_mask};
+    DevBuf<uint32_t> large;  // fast path: members of large groups that the register sort left alone
+    if (fast2) {
+        large = dalloc<uint32_t>(r0n / 32 + 1);
+        SUFR_CUDA_CHECK(cudaMemsetAsync(large.get(), 0, (r0n / 32 + 1) * 4, st()));
+        fast2_group_sort_kernel<<<grid_for(r0n, 2), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+    }
+    ViewAll v0{keys_sorted.get(), d_sa.get(), fast2 ? large.get() : nullptr};
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, pos, seg;
     {
@@ -562,7 +569,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         auto d_cnt = dalloc<unsigned long long>(1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
         if (fast2) {
-            resolve0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks,
+            resolve0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get(),
                                                                         d_lcp.get(), act_slot.get(), act_pos.get(),
                                                                         d_cnt.get(), capacity);
         } else {
@@ -594,8 +601,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             slot = std::move(act_slot);
             pos = std::move(act_pos);
             seg = dalloc<uint32_t>(m);
-            nseg = scan_total(m, SparseSegIn{keys_sorted.get(), slot.get(), cmp_mask}, scan::SumU32{},
-                              SparseSegOut{seg.get()});
+            nseg = scan_total(m, SparseSegIn{v0, slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
         } else {
             // dense (repetitive text): order-preserving compaction by scan
             act_slot.reset();

@@ -369,8 +369,10 @@ __global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n
 struct ViewAll {
     const uint64_t* key;
     const uint32_t* pos;
-    uint64_t cmp_mask;  // ~0, or the sorted top bits of the 2-bit fast path
-    __device__ uint64_t k(uint64_t i) const { return key[i] & cmp_mask; }
+    const uint32_t* large;  // fast path: bitmap of the members of large, only partially sorted groups (else NULL)
+    __device__ uint64_t k(uint64_t i) const {
+        return large ? fast2_canon(key[i], (large[i >> 5] >> (i & 31)) & 1u) : key[i];
+    }
     __device__ uint64_t raw(uint64_t i) const { return key[i]; }
     __device__ uint32_t p(uint64_t i) const { return pos[i]; }
     __device__ bool same_seg(uint64_t i) const { return i > 0; }
@@ -484,14 +486,54 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
     }
 }
 
-// Round 0 of the 2-bit fast path.  Only the top kFast2SortBits of the keys are sorted: a group is a run of
-// equal sorted bits, everything in a group of size > 1 is collected for the exact refinement (which starts
-// at key word 0).  Boundary LCP = clz(x ^ y) / 2 when neither key contains fill, else an exact comparison
-// on the packed text.  Filtered suffixes (key ~0) are inside the last group and never collected... they are
-// collected with it (the refinement sorts them to the very end of the array and then drops them).
+// Fast path, after the 4-pass radix sort on the top kFast2SortBits: the thread at the start of every group of
+// 2..kFast2SmallGroup keys that tie on the sorted bits orders the group by the full keys in registers (in place).
+// Members of larger groups are marked in the `large` bitmap and left to the refinement.
+__global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __restrict__ keys,
+                                                                  uint32_t* __restrict__ pos, uint64_t s,
+                                                                  uint32_t* __restrict__ large) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+        const uint64_t kj = keys[j];
+        const uint64_t top = kj & kFast2TopMask;
+        // any window of kFast2SmallGroup + 1 equal elements lies inside a large group: mark it
+        if (j + kFast2SmallGroup < s && (keys[j + kFast2SmallGroup] & kFast2TopMask) == top) {
+            for (uint64_t t = j; t <= j + kFast2SmallGroup; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
+        }
+        if (j > 0 && (keys[j - 1] & kFast2TopMask) == top) continue;  // not the first of its group
+        int len = 1;
+        while (len <= kFast2SmallGroup && j + len < s && (keys[j + len] & kFast2TopMask) == top) len++;
+        if (len == 1 || len > kFast2SmallGroup) continue;
+        uint64_t k[kFast2SmallGroup];
+        uint32_t p[kFast2SmallGroup];
+#pragma unroll
+        for (int i = 0; i < kFast2SmallGroup; i++) {
+            k[i] = i < len ? keys[j + i] : ~0ull;
+            p[i] = i < len ? pos[j + i] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < kFast2SmallGroup; i++) {
+            if (i < len) {
+                int r = 0;
+#pragma unroll
+                for (int t = 0; t < kFast2SmallGroup; t++)
+                    if (t < len && (k[t] < k[i] || (k[t] == k[i] && t < i))) r++;
+                keys[j + r] = k[i];
+                pos[j + r] = p[i];
+            }
+        }
+    }
+}
+
+// Round 0 of the 2-bit fast path, on the array ordered by fast2_group_sort_kernel.  A group is a run of equal
+// canonical keys (fast2_canon): exact ties on all 31 symbols, or the members of a large group.  Everything in
+// a group of size > 1 is collected for the exact refinement (which starts at key word 0).  Boundary LCP =
+// clz(x ^ y) / 2 when neither key contains fill and both neighbours are final (singleton groups), else it is
+// recomputed from the final order (kLcpFixup).  Filtered suffixes (key ~0) sort behind everything.
 __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* __restrict__ keys,
                                                                 const uint32_t* __restrict__ pos, uint64_t s,
-                                                                KeySpec ks, uint32_t* __restrict__ lcp,
+                                                                const uint32_t* __restrict__ large,
+                                                                uint32_t* __restrict__ lcp,
                                                                 uint32_t* __restrict__ act_slot,
                                                                 uint32_t* __restrict__ act_pos,
                                                                 unsigned long long* __restrict__ act_count,
@@ -499,26 +541,27 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
     __shared__ uint32_t wcount[kBlock / 32];
     __shared__ unsigned long long gbase;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    auto canon = [&](uint64_t i) { return fast2_canon(keys[i], (large[i >> 5] >> (i & 31)) & 1u); };
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < s; base += stride) {
         const uint64_t j = base + threadIdx.x;
         bool active = false;
         uint32_t p = 0;
         if (j < s) {
-            uint64_t kj = keys[j];
+            const uint64_t kj = keys[j];
+            const uint64_t cj = canon(j);
             p = pos[j];
             bool head = true;
-            bool next_same = j + 1 < s && ((keys[j + 1] ^ kj) & kFast2CmpMask) == 0;
+            const bool next_same = j + 1 < s && canon(j + 1) == cj;
             if (j == 0) {
                 lcp[0] = 0;
             } else {
-                uint64_t kp = keys[j - 1];
-                head = ((kp ^ kj) & kFast2CmpMask) != 0;
+                const uint64_t kp = keys[j - 1];
+                const uint64_t cp = canon(j - 1);
+                head = cp != cj;
                 if (!head) {
                     lcp[j] = kLcpPending;
                 } else {
-                    // The LCP of a boundary can be read off the two keys only if neither contains fill and the
-                    // final neighbours are already known, i.e. both adjacent groups are singletons.
-                    bool prev_multi = j >= 2 && ((keys[j - 2] ^ kp) & kFast2CmpMask) == 0;
+                    const bool prev_multi = j >= 2 && canon(j - 2) == cp;
                     if (((kp | kj) & 1ull) == 0 && !next_same && !prev_multi)
                         lcp[j] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
                     else
@@ -542,12 +585,11 @@ __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t 
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
 // previous SA slot's key
 struct SparseSegIn {
-    const uint64_t* keys;
+    ViewAll v;  // group keys of the sorted array
     const uint32_t* slot;
-    uint64_t cmp_mask;
     __device__ uint32_t operator()(uint64_t a) const {
         uint32_t j = slot[a];
-        return (j == 0 || ((keys[j] ^ keys[j - 1]) & cmp_mask) != 0) ? 1u : 0u;
+        return (j == 0 || v.k(j) != v.k(j - 1)) ? 1u : 0u;
     }
 };
 struct SparseSegOut {

@@ -45,11 +45,19 @@ struct KeySpec {
 };
 
 // Fast-path keys: bit 0 = the key contains fill (an irregular symbol inside its 31-symbol window),
-// bits 63..2 = 31 symbols.  Only the top kFast2SortBits are sorted; everything that ties on them is
-// re-sorted by the exact 3-bit key words.
+// bits 63..2 = 31 symbols.  The radix sort covers only the top kFast2SortBits (4 passes); groups of up to
+// kFast2SmallGroup keys that tie on those bits are then ordered by their full keys in registers
+// (fast2_group_sort_kernel), larger groups and exact ties on all 31 symbols go to the 3-bit refinement.
 constexpr int kFast2Symbols = 31;
-constexpr int kFast2SortBits = 40;
-constexpr uint64_t kFast2CmpMask = ~0ull << (64 - kFast2SortBits);
+constexpr int kFast2SortBits = 32;
+constexpr int kFast2ProbeBits = 40;  // the repetitiveness probe sorts its sample deeper
+constexpr int kFast2SmallGroup = 8;
+constexpr uint64_t kFast2TopMask = ~0ull << (64 - kFast2SortBits);
+// Group key of a sorted element: members of a large (unsorted) group agree on the sorted bits only, everything
+// else is ordered by the full symbol bits.
+__host__ __device__ __forceinline__ uint64_t fast2_canon(uint64_t key, bool large) {
+    return large ? (key & kFast2TopMask) : (key & ~3ull);
+}
 
 __device__ __forceinline__ void split_pos(const PackedText& pt, uint64_t p, uint64_t& q, uint32_t& r) {
     if (pt.n <= 0xFFFFFFFFull) {
