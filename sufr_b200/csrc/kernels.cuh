@@ -492,18 +492,66 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
 __global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __restrict__ keys,
                                                                   uint32_t* __restrict__ pos, uint64_t s,
                                                                   uint32_t* __restrict__ large) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
-        const uint64_t kj = keys[j];
-        const uint64_t top = kj & kFast2TopMask;
-        // any window of kFast2SmallGroup + 1 equal elements lies inside a large group: mark it
-        if (j + kFast2SmallGroup < s && (keys[j + kFast2SmallGroup] & kFast2TopMask) == top) {
-            for (uint64_t t = j; t <= j + kFast2SmallGroup; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
+    // Four consecutive elements per thread: the streaming part (own keys, predecessor, the keys
+    // kFast2SmallGroup ahead) is 16-byte loads issued together; only group heads do scattered work.
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < s; j0 += stride) {
+        uint64_t kk[4], kw[4];
+        if (j0 + 3 < s) {
+            ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + j0);
+            ulonglong2 c = *reinterpret_cast<const ulonglong2*>(keys + j0 + 2);
+            kk[0] = a.x; kk[1] = a.y; kk[2] = c.x; kk[3] = c.y;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) kk[u] = j0 + u < s ? keys[j0 + u] : 0ull;
         }
-        if (j > 0 && (keys[j - 1] & kFast2TopMask) == top) continue;  // not the first of its group
+        if (j0 + kFast2SmallGroup + 3 < s) {
+            ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + j0 + kFast2SmallGroup);
+            ulonglong2 c = *reinterpret_cast<const ulonglong2*>(keys + j0 + kFast2SmallGroup + 2);
+            kw[0] = a.x; kw[1] = a.y; kw[2] = c.x; kw[3] = c.y;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) kw[u] = j0 + u + kFast2SmallGroup < s ? keys[j0 + u + kFast2SmallGroup] : 0ull;
+        }
+        const uint64_t kprev = j0 ? keys[j0 - 1] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t j = j0 + u;
+            if (j >= s) break;
+            const uint64_t kj = kk[u];
+            const uint64_t top = kj & kFast2TopMask;
+            // any window of kFast2SmallGroup + 1 equal elements lies inside a large group: mark it
+            if (j + kFast2SmallGroup < s && (kw[u] & kFast2TopMask) == top) {
+                for (uint64_t t = j; t <= j + kFast2SmallGroup; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
+            }
+            const uint64_t kp = u ? kk[u - 1] : kprev;
+            if (j > 0 && (kp & kFast2TopMask) == top) continue;  // not the first of its group
         int len = 1;
         while (len <= kFast2SmallGroup && j + len < s && (keys[j + len] & kFast2TopMask) == top) len++;
         if (len == 1 || len > kFast2SmallGroup) continue;
+        // Groups of 2, 3 and 4 (almost all of them) take compare-exchange networks and write back only what
+        // moved; 5..kFast2SmallGroup take the generic rank sort.
+        if (len <= 4) {
+            uint64_t k0 = kj, k1 = keys[j + 1], k2 = len > 2 ? keys[j + 2] : ~0ull, k3 = len > 3 ? keys[j + 3] : ~0ull;
+            if (k0 <= k1 && k1 <= k2 && k2 <= k3) continue;  // already in order (half of the pairs)
+            uint32_t p0 = pos[j], p1 = pos[j + 1], p2 = len > 2 ? pos[j + 2] : 0u, p3 = len > 3 ? pos[j + 3] : 0u;
+#define SUFR_CAS(ka, pa, kb, pb)                         \
+    if (kb < ka) {                                       \
+        uint64_t tk = ka; ka = kb; kb = tk;              \
+        uint32_t tp = pa; pa = pb; pb = tp;              \
+    }
+            SUFR_CAS(k0, p0, k1, p1)
+            SUFR_CAS(k2, p2, k3, p3)
+            SUFR_CAS(k0, p0, k2, p2)
+            SUFR_CAS(k1, p1, k3, p3)
+            SUFR_CAS(k1, p1, k2, p2)
+#undef SUFR_CAS
+            keys[j] = k0; pos[j] = p0;
+            keys[j + 1] = k1; pos[j + 1] = p1;
+            if (len > 2) { keys[j + 2] = k2; pos[j + 2] = p2; }
+            if (len > 3) { keys[j + 3] = k3; pos[j + 3] = p3; }
+            continue;
+        }
         uint64_t k[kFast2SmallGroup];
         uint32_t p[kFast2SmallGroup];
 #pragma unroll
@@ -522,6 +570,7 @@ __global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __re
                 pos[j + r] = p[i];
             }
         }
+        }
     }
 }
 
@@ -538,48 +587,132 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
                                                                 uint32_t* __restrict__ act_pos,
                                                                 unsigned long long* __restrict__ act_count,
                                                                 uint64_t capacity) {
+    // Four consecutive elements per thread (16-byte loads of keys / positions, one 16-byte LCP store); the
+    // flagged elements of a block iteration (1024 elements) are appended with one global atomic.
     __shared__ uint32_t wcount[kBlock / 32];
     __shared__ unsigned long long gbase;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    auto canon = [&](uint64_t i) { return fast2_canon(keys[i], (large[i >> 5] >> (i & 31)) & 1u); };
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < s; base += stride) {
-        const uint64_t j = base + threadIdx.x;
-        bool active = false;
-        uint32_t p = 0;
-        if (j < s) {
-            const uint64_t kj = keys[j];
-            const uint64_t cj = canon(j);
-            p = pos[j];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    auto is_large = [&](uint64_t i) { return ((large[i >> 5] >> (i & 31)) & 1u) != 0; };
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * 4; base < s; base += stride) {
+        const uint64_t j0 = base + (uint64_t)threadIdx.x * 4;
+        // canonical keys of j0-2 .. j0+4 (index 0 <-> j0-2); raw keys of j0-1 .. j0+3
+        uint64_t c[7], raw[5];
+        uint32_t pp[4] = {0, 0, 0, 0};
+        bool valid[7];
+#pragma unroll
+        for (int t = 0; t < 7; t++) {
+            const long long i = (long long)j0 + t - 2;
+            valid[t] = i >= 0 && (uint64_t)i < s;
+        }
+        if (j0 + 3 < s) {
+            ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + j0);
+            ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(keys + j0 + 2);
+            uint4 p4 = *reinterpret_cast<const uint4*>(pos + j0);
+            raw[1] = a.x; raw[2] = a.y; raw[3] = b2.x; raw[4] = b2.y;
+            pp[0] = p4.x; pp[1] = p4.y; pp[2] = p4.z; pp[3] = p4.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                raw[1 + u] = j0 + u < s ? keys[j0 + u] : 0ull;
+                pp[u] = j0 + u < s ? pos[j0 + u] : 0u;
+            }
+        }
+        raw[0] = valid[1] ? keys[j0 - 1] : 0ull;
+        const uint64_t km2 = valid[0] ? keys[j0 - 2] : 0ull;
+        const uint64_t kp4 = valid[6] ? keys[j0 + 4] : 0ull;
+        c[0] = valid[0] ? fast2_canon(km2, is_large(j0 - 2)) : 0ull;
+#pragma unroll
+        for (int t = 1; t < 6; t++) c[t] = valid[t] ? fast2_canon(raw[t - 1], is_large(j0 + t - 2)) : 0ull;
+        c[6] = valid[6] ? fast2_canon(kp4, is_large(j0 + 4)) : 0ull;
+
+        uint32_t out[4] = {0, 0, 0, 0};
+        uint32_t act = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t j = j0 + u;
+            if (j >= s) break;
+            const int t = u + 2;  // index of element j in c[]
+            const bool next_same = valid[t + 1] && c[t + 1] == c[t];
             bool head = true;
-            const bool next_same = j + 1 < s && canon(j + 1) == cj;
             if (j == 0) {
-                lcp[0] = 0;
+                out[u] = 0;
             } else {
-                const uint64_t kp = keys[j - 1];
-                const uint64_t cp = canon(j - 1);
-                head = cp != cj;
+                head = c[t - 1] != c[t];
                 if (!head) {
-                    lcp[j] = kLcpPending;
+                    out[u] = kLcpPending;
                 } else {
-                    const bool prev_multi = j >= 2 && canon(j - 2) == cp;
+                    const bool prev_multi = valid[t - 2] && j >= 2 && c[t - 2] == c[t - 1];
+                    const uint64_t kp = raw[u], kj = raw[u + 1];
                     if (((kp | kj) & 1ull) == 0 && !next_same && !prev_multi)
-                        lcp[j] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
+                        out[u] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
                     else
-                        lcp[j] = kLcpFixup;
+                        out[u] = kLcpFixup;
                 }
             }
-            active = !head || next_same;
+            if (!head || next_same) act |= 1u << u;
         }
-        block_append(active, (uint32_t)j, p, act_slot, act_pos, act_count, capacity, wcount, &gbase);
+        if (j0 + 3 < s) {
+            *reinterpret_cast<uint4*>(lcp + j0) = make_uint4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (j0 + u < s) lcp[j0 + u] = out[u];
+        }
+        // append: per-thread count -> warp prefix -> block prefix -> one atomic
+        const uint32_t mine = __popc(act);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (lane == 31) wcount[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int w = 0; w < kBlock / 32; w++) {
+                uint32_t tt = wcount[w];
+                wcount[w] = acc;
+                acc += tt;
+            }
+            gbase = acc ? atomicAdd(act_count, (unsigned long long)acc) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long idx = gbase + wcount[warp] + incl - mine;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (act & (1u << u)) {
+                if (idx < capacity) {
+                    act_slot[idx] = (uint32_t)(j0 + u);
+                    act_pos[idx] = pp[u];
+                }
+                idx++;
+            }
+        }
+        __syncthreads();
     }
 }
 
 // Exact LCP of the boundaries the fast path could not read off the keys, from the FINAL suffix order.
 __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
                                                            uint32_t* __restrict__ lcp) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride)
-        if (lcp[j] == kLcpFixup) lcp[j] = j ? (uint32_t)lcp_direct(ks, sa[j - 1], sa[j], 0) : 0u;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < s; j0 += stride) {
+        uint32_t v[4];
+        if (j0 + 3 < s) {
+            uint4 x = *reinterpret_cast<const uint4*>(lcp + j0);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = j0 + u < s ? lcp[j0 + u] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t j = j0 + u;
+            if (j < s && v[u] == kLcpFixup) lcp[j] = j ? (uint32_t)lcp_direct(ks, sa[j - 1], sa[j], 0) : 0u;
+        }
+    }
 }
 
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
