@@ -554,7 +554,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     if (fast2) {
         large = dalloc<uint32_t>(r0n / 32 + 1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(large.get(), 0, (r0n / 32 + 1) * 4, st()));
-        fast2_group_sort_kernel<<<grid_for(r0n, 2), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get());
+        fast2_group_sort_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get());
         SUFR_KERNEL_CHECK();
         launched();
     }

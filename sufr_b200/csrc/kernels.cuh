@@ -486,90 +486,98 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
     }
 }
 
-// Fast path, after the 4-pass radix sort on the top kFast2SortBits: the thread at the start of every group of
-// 2..kFast2SmallGroup keys that tie on the sorted bits orders the group by the full keys in registers (in place).
-// Members of larger groups are marked in the `large` bitmap and left to the refinement.
+// Fast path, after the 4-pass radix sort on the top kFast2SortBits: every group of 2..kFast2SmallGroup keys that
+// tie on the sorted bits is ordered by the full keys.  Tiled: a block stages 1024 records (+ a halo of
+// kFast2SmallGroup) in shared memory with coalesced loads, the thread at the start of each group orders it there
+// (compare-exchange networks for 2..4, rank sort for 5..8), and the tile is written back coalesced.  A group is
+// owned by the tile that holds its first element.  Members of larger groups are marked in the `large` bitmap
+// and left to the refinement.
+constexpr int kGroupTile = 1024;
 __global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __restrict__ keys,
                                                                   uint32_t* __restrict__ pos, uint64_t s,
                                                                   uint32_t* __restrict__ large) {
-    // Four consecutive elements per thread: the streaming part (own keys, predecessor, the keys
-    // kFast2SmallGroup ahead) is 16-byte loads issued together; only group heads do scattered work.
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
-    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < s; j0 += stride) {
-        uint64_t kk[4], kw[4];
-        if (j0 + 3 < s) {
-            ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + j0);
-            ulonglong2 c = *reinterpret_cast<const ulonglong2*>(keys + j0 + 2);
-            kk[0] = a.x; kk[1] = a.y; kk[2] = c.x; kk[3] = c.y;
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; u++) kk[u] = j0 + u < s ? keys[j0 + u] : 0ull;
+    constexpr int H = kFast2SmallGroup;
+    constexpr int N = kGroupTile + H;  // local index i <-> global t0 + i
+    __shared__ uint64_t sk[N + 1];     // sk[N]: unused pad
+    __shared__ uint32_t sp[N + 1];
+    __shared__ uint32_t first_owned;   // local index of the first element whose group starts in this tile
+    const uint64_t tiles = (s + kGroupTile - 1) / kGroupTile;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * kGroupTile;
+        const uint32_t cnt = (uint32_t)((s - t0) < (uint64_t)N ? (s - t0) : (uint64_t)N);   // staged records
+        const uint32_t own = (uint32_t)((s - t0) < (uint64_t)kGroupTile ? (s - t0) : (uint64_t)kGroupTile);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) {
+            sk[i] = keys[t0 + i];
+            sp[i] = pos[t0 + i];
         }
-        if (j0 + kFast2SmallGroup + 3 < s) {
-            ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + j0 + kFast2SmallGroup);
-            ulonglong2 c = *reinterpret_cast<const ulonglong2*>(keys + j0 + kFast2SmallGroup + 2);
-            kw[0] = a.x; kw[1] = a.y; kw[2] = c.x; kw[3] = c.y;
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; u++) kw[u] = j0 + u + kFast2SmallGroup < s ? keys[j0 + u + kFast2SmallGroup] : 0ull;
-        }
-        const uint64_t kprev = j0 ? keys[j0 - 1] : 0ull;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint64_t j = j0 + u;
-            if (j >= s) break;
-            const uint64_t kj = kk[u];
-            const uint64_t top = kj & kFast2TopMask;
-            // any window of kFast2SmallGroup + 1 equal elements lies inside a large group: mark it
-            if (j + kFast2SmallGroup < s && (kw[u] & kFast2TopMask) == top) {
-                for (uint64_t t = j; t <= j + kFast2SmallGroup; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
-            }
-            const uint64_t kp = u ? kk[u - 1] : kprev;
-            if (j > 0 && (kp & kFast2TopMask) == top) continue;  // not the first of its group
-        int len = 1;
-        while (len <= kFast2SmallGroup && j + len < s && (keys[j + len] & kFast2TopMask) == top) len++;
-        if (len == 1 || len > kFast2SmallGroup) continue;
-        // Groups of 2, 3 and 4 (almost all of them) take compare-exchange networks and write back only what
-        // moved; 5..kFast2SmallGroup take the generic rank sort.
-        if (len <= 4) {
-            uint64_t k0 = kj, k1 = keys[j + 1], k2 = len > 2 ? keys[j + 2] : ~0ull, k3 = len > 3 ? keys[j + 3] : ~0ull;
-            if (k0 <= k1 && k1 <= k2 && k2 <= k3) continue;  // already in order (half of the pairs)
-            uint32_t p0 = pos[j], p1 = pos[j + 1], p2 = len > 2 ? pos[j + 2] : 0u, p3 = len > 3 ? pos[j + 3] : 0u;
+        const uint64_t top_before = t0 ? (keys[t0 - 1] & kFast2TopMask) : 0ull;
+        if (threadIdx.x == 0) first_owned = own;
+        __syncthreads();
+        // heads: first element of a run of equal sorted bits
+        for (uint32_t i = threadIdx.x; i < own; i += kBlock) {
+            const uint64_t top = sk[i] & kFast2TopMask;
+            // any window of H + 1 equal elements lies inside a large group: mark it
+            if (i + H < cnt && (sk[i + H] & kFast2TopMask) == top)
+                for (uint64_t t = t0 + i; t <= t0 + i + H; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
+            const bool head = i ? ((sk[i - 1] & kFast2TopMask) != top) : (t0 == 0 || top_before != top);
+            if (!head) continue;
+            atomicMin(&first_owned, i);
+            uint32_t len = 1;
+            while (len <= (uint32_t)H && i + len < cnt && (sk[i + len] & kFast2TopMask) == top) len++;
+            if (len == 1 || len > (uint32_t)H) continue;
+            if (len <= 4) {
+                uint64_t k0 = sk[i], k1 = sk[i + 1], k2 = len > 2 ? sk[i + 2] : ~0ull, k3 = len > 3 ? sk[i + 3] : ~0ull;
+                if (k0 <= k1 && k1 <= k2 && k2 <= k3) continue;
+                uint32_t p0 = sp[i], p1 = sp[i + 1], p2 = len > 2 ? sp[i + 2] : 0u, p3 = len > 3 ? sp[i + 3] : 0u;
 #define SUFR_CAS(ka, pa, kb, pb)                         \
     if (kb < ka) {                                       \
         uint64_t tk = ka; ka = kb; kb = tk;              \
         uint32_t tp = pa; pa = pb; pb = tp;              \
     }
-            SUFR_CAS(k0, p0, k1, p1)
-            SUFR_CAS(k2, p2, k3, p3)
-            SUFR_CAS(k0, p0, k2, p2)
-            SUFR_CAS(k1, p1, k3, p3)
-            SUFR_CAS(k1, p1, k2, p2)
+                SUFR_CAS(k0, p0, k1, p1)
+                SUFR_CAS(k2, p2, k3, p3)
+                SUFR_CAS(k0, p0, k2, p2)
+                SUFR_CAS(k1, p1, k3, p3)
+                SUFR_CAS(k1, p1, k2, p2)
 #undef SUFR_CAS
-            keys[j] = k0; pos[j] = p0;
-            keys[j + 1] = k1; pos[j + 1] = p1;
-            if (len > 2) { keys[j + 2] = k2; pos[j + 2] = p2; }
-            if (len > 3) { keys[j + 3] = k3; pos[j + 3] = p3; }
-            continue;
-        }
-        uint64_t k[kFast2SmallGroup];
-        uint32_t p[kFast2SmallGroup];
+                sk[i] = k0; sp[i] = p0;
+                sk[i + 1] = k1; sp[i + 1] = p1;
+                if (len > 2) { sk[i + 2] = k2; sp[i + 2] = p2; }
+                if (len > 3) { sk[i + 3] = k3; sp[i + 3] = p3; }
+                continue;
+            }
+            uint64_t k[H];
+            uint32_t p[H];
 #pragma unroll
-        for (int i = 0; i < kFast2SmallGroup; i++) {
-            k[i] = i < len ? keys[j + i] : ~0ull;
-            p[i] = i < len ? pos[j + i] : 0u;
-        }
+            for (int e = 0; e < H; e++) {
+                k[e] = (uint32_t)e < len ? sk[i + e] : ~0ull;
+                p[e] = (uint32_t)e < len ? sp[i + e] : 0u;
+            }
 #pragma unroll
-        for (int i = 0; i < kFast2SmallGroup; i++) {
-            if (i < len) {
-                int r = 0;
+            for (int e = 0; e < H; e++) {
+                if ((uint32_t)e < len) {
+                    int r = 0;
 #pragma unroll
-                for (int t = 0; t < kFast2SmallGroup; t++)
-                    if (t < len && (k[t] < k[i] || (k[t] == k[i] && t < i))) r++;
-                keys[j + r] = k[i];
-                pos[j + r] = p[i];
+                    for (int t = 0; t < H; t++)
+                        if ((uint32_t)t < len && (k[t] < k[e] || (k[t] == k[e] && t < e))) r++;
+                    sk[i + r] = k[e];
+                    sp[i + r] = p[e];
+                }
             }
         }
+        __syncthreads();
+        // write back what this tile owns: from its first head up to the end of the last group it started
+        // (that group may reach into the halo; the leading elements of the tile belong to the previous tile)
+        uint32_t last = own;
+        if (first_owned >= own) continue;  // no group starts here (uniform branch: shared value)
+        if (own == (uint32_t)kGroupTile && cnt > own) {
+            const uint64_t top_last = sk[own - 1] & kFast2TopMask;
+            while (last < cnt && (sk[last] & kFast2TopMask) == top_last) last++;
+        }
+        for (uint32_t i = first_owned + threadIdx.x; i < last; i += kBlock) {
+            keys[t0 + i] = sk[i];
+            pos[t0 + i] = sp[i];
         }
     }
 }
