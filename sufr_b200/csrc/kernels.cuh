@@ -512,8 +512,12 @@ __global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __re
             sp[i] = pos[t0 + i];
         }
         const uint64_t top_before = t0 ? (keys[t0 - 1] & kFast2TopMask) : 0ull;
-        if (threadIdx.x == 0) first_owned = own;
         __syncthreads();
+        if (threadIdx.x == 0) {  // elements that continue the previous tile's last group are not owned
+            uint32_t lead = 0;
+            if (t0) while (lead < own && (sk[lead] & kFast2TopMask) == top_before) lead++;
+            first_owned = lead;
+        }
         // heads: first element of a run of equal sorted bits
         for (uint32_t i = threadIdx.x; i < own; i += kBlock) {
             const uint64_t top = sk[i] & kFast2TopMask;
@@ -522,7 +526,6 @@ __global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __re
                 for (uint64_t t = t0 + i; t <= t0 + i + H; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
             const bool head = i ? ((sk[i - 1] & kFast2TopMask) != top) : (t0 == 0 || top_before != top);
             if (!head) continue;
-            atomicMin(&first_owned, i);
             uint32_t len = 1;
             while (len <= (uint32_t)H && i + len < cnt && (sk[i + len] & kFast2TopMask) == top) len++;
             if (len == 1 || len > (uint32_t)H) continue;
