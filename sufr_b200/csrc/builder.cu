@@ -166,6 +166,8 @@ class Build {
     DevBuf<uint32_t> d_counts;  // radix sort count matrix
     uint64_t shard_offset = 0, shard_count = 0, total_suffixes = 0;
     bool layout_exact_ = true;  // shard_offset / total_suffixes are known without an exchange
+    bool cuts_ready_ = false;   // the shard's key range has been fixed (first histogram of this build)
+    uint32_t cut_b0_ = 0, cut_b1_ = 0;
     bool full_set_ = true;  // every text position is being sorted on this rank (prefix doubling needs that)
     int t_keys_mark = -1, t_sorted_mark = -1;
     rsort::EventPairs downsweep_events;
@@ -396,10 +398,11 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         // Splitters from a histogram of the top 12 key bits: every rank computes the same histogram of the
         // replicated text, so ranks agree on the key ranges without communicating.  The full sort only needs
         // balanced ranges, so it histograms every 16th position; the modes whose tie order depends on the
-        // input order (mask / max-query-len) and the slicing fallback use the exact histogram, which also
-        // yields the exact shard offsets.
+        // input order (mask / max-query-len) use the exact histogram, which also yields the exact shard
+        // offsets.  The cut points are fixed by the FIRST histogram of a build: the full-sort fallback (which
+        // only some ranks may take) re-counts exactly but keeps the same cuts.
         const uint32_t hbits = 12, bins = 1u << hbits;
-        const bool exact = ks.mode != kModeFull || !sharded;
+        const bool exact = ks.mode != kModeFull || cuts_ready_;
         const uint32_t sample_shift = exact ? 0 : 4;
         auto d_hist = dalloc<unsigned long long>(bins);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_hist.get(), 0, bins * 8, st()));
@@ -412,18 +415,24 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         std::vector<unsigned long long> hist(bins);
         SUFR_CUDA_CHECK(cudaMemcpyAsync(hist.data(), d_hist.get(), bins * 8, cudaMemcpyDeviceToHost, st()));
         SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
-        // bin boundaries b_0 = 0 <= b_1 <= ... <= b_world = bins with balanced counts
-        // (counts are of INDEXED suffixes, so shard offsets refer to the final suffix array)
-        std::vector<uint32_t> cut(world + 1, bins);
-        cut[0] = 0;
-        unsigned long long total = 0, acc = 0;
+        unsigned long long total = 0;
         for (uint32_t b = 0; b < bins; b++) total += hist[b];
-        int g = 1;
-        for (uint32_t b = 0; b < bins && g < world; b++) {
-            acc += hist[b];
-            while (g < world && acc * world >= total * g) cut[g++] = b + 1;
+        if (!cuts_ready_) {
+            // bin boundaries b_0 = 0 <= b_1 <= ... <= b_world = bins with balanced counts
+            // (counts are of INDEXED suffixes, so shard offsets refer to the final suffix array)
+            std::vector<uint32_t> cut(world + 1, bins);
+            cut[0] = 0;
+            unsigned long long acc = 0;
+            int g = 1;
+            for (uint32_t b = 0; b < bins && g < world; b++) {
+                acc += hist[b];
+                while (g < world && acc * world >= total * g) cut[g++] = b + 1;
+            }
+            cut_b0_ = cut[args.rank];
+            cut_b1_ = cut[args.rank + 1];
+            cuts_ready_ = true;
         }
-        uint32_t b0 = cut[args.rank], b1 = cut[args.rank + 1];
+        const uint32_t b0 = cut_b0_, b1 = cut_b1_;
         unsigned long long before = 0, mine = 0;
         for (uint32_t b = 0; b < b0; b++) before += hist[b];
         for (uint32_t b = b0; b < b1; b++) mine += hist[b];

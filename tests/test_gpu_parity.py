@@ -489,3 +489,28 @@ def test_filter_after_full_sort_fast_and_generic_paths(S, monkeypatch):
     monkeypatch.delenv("SUFR_B200_DEBUG_SLOW_FILTER")
     text2 = base[:20000] + b"N" * 3000 + base[:20000] + b"N" * 700 + base[5000:15000] + b"$"
     gpu_vs_oracle(S, text2, is_dna=True)
+
+
+def test_sharded_fallback_on_some_ranks_only(S):
+    """Found by tools/stress.py: when only SOME ranks hit deep repeats (long N runs under --allow-ambiguity)
+    and redo their build unsharded, they must keep the key-range cuts every rank derived first."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = np.random.default_rng(11)
+    t = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 120000)].copy()
+    t[30000:32200] = ord("N")
+    t[90000:91001] = ord("N")
+    text = t.tobytes() + b"$"
+    for flags in (dict(is_dna=True, allow_ambiguity=True), dict(is_dna=True, allow_ambiguity=True, ignore_softmask=True)):
+        want = O.oracle_build(text, threads=4, **flags)
+        for world in (2, 3, 5):
+            shards = [S.build(S.SufrBuilderArgs(text=text, **flags), rank=r, world_size=world) for r in range(world)]
+            meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+            offs, total = shard_layout(meta)
+            assert total == want.num_suffixes
+            for r, s in enumerate(shards):
+                s.set_shard_layout(offs[r], total)
+                prev = previous_last_suffix(meta, r)
+                if prev is not None and s.num_suffixes:
+                    s.patch_seam(prev)
+            assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
+            assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
