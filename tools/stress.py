@@ -32,7 +32,7 @@ def make_text(rng: random.Random, n: int):
         t[t == ord("$")] = ord("A")
     else:
         t = np.frombuffer(b"ACGT", np.uint8)[np_rng.integers(0, 4, n)].copy()
-        if kind in ("dna_rare", "dna_n", "repeat", "tandem"):
+        if kind in ("dna_rare", "repeat", "tandem") or (kind == "dna_n" and rng.random() < 0.5):
             rare = np.frombuffer(b"N%RYnacgt#~" if kind != "dna_n" else b"N", np.uint8)
             k = max(1, int(n * rng.choice([0.0005, 0.01, 0.08])))
             t[np_rng.integers(0, n, k)] = rare[np_rng.integers(0, len(rare), k)]
@@ -67,6 +67,7 @@ def main():
     args = ap.parse_args()
     rng = random.Random(args.seed)
     failures = 0
+    skipped = 0
     t0 = time.time()
     for case in range(args.cases):
         n = int(10 ** rng.uniform(1.0, np.log10(args.max_n)))
@@ -90,6 +91,16 @@ def main():
             want = O.oracle_build(text, num_partitions=1 if len(text) < 4000 else 16, threads=4, index_bits=bits, **flags)
         except O.OracleError as e:
             continue
+        if want.n_ranges and not flags.get("seed_mask"):
+            # The reference is only a function of its input when every N-prefixed suffix lies in a recorded run
+            # (SURVEY 8a rule 3) and no max-query-len cap interferes with the N-run shortcut: skip the rest.
+            t = np.frombuffer(want.text, np.uint8)
+            in_run = np.zeros(len(t), bool)
+            for a, b in want.n_ranges:
+                in_run[a:b] = True
+            if flags.get("max_query_len") or bool(((t == ord("N")) & ~in_run).any()):
+                skipped += 1
+                continue
         bargs = S.SufrBuilderArgs(text=text, **flags)
         try:
             if world == 1:
@@ -121,7 +132,8 @@ def main():
             bad_lcp = int(np.nonzero(lcp != want.lcp)[0][0]) if len(lcp) == len(want.lcp) and (lcp != want.lcp).any() else -1
             print(f"FAIL case {case}: kind={kind} n={len(text)} flags={flags} bits={bits} world={world} "
                   f"first_sa_diff={bad_sa} first_lcp_diff={bad_lcp} sizes={len(sa)}/{len(want.sa)}", flush=True)
-    print(f"{args.cases} cases, {failures} failures, {time.time() - t0:.1f}s")
+    print(f"{args.cases} cases, {failures} failures, {skipped} skipped as ill-defined for the reference, "
+          f"{time.time() - t0:.1f}s")
     sys.exit(1 if failures else 0)
 
 
