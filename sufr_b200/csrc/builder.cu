@@ -1233,9 +1233,20 @@ int sufr_b200_patch_seam(SufrB200Ctx* c, const SufrB200Args* args, SufrB200Resul
                 SUFR_CUDA_CHECK(cudaMemcpyAsync(dst, r->text + p, len, cudaMemcpyDeviceToHost, ctx->stream));
                 SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
             } else {
+                // raw text of the caller (host or device memory, as it was passed to the build) + the transform
                 if (!args->text) throw Error(SUFR_B200_ERR_ARGUMENT, "patch_seam needs the text (result or args)");
+                cudaPointerAttributes attr{};
+                bool on_device = cudaPointerGetAttributes(&attr, args->text) == cudaSuccess &&
+                                 (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+                cudaGetLastError();
+                if (on_device) {
+                    SUFR_CUDA_CHECK(cudaMemcpyAsync(dst, args->text + p, len, cudaMemcpyDeviceToHost, ctx->stream));
+                    SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                } else {
+                    memcpy(dst, args->text + p, len);
+                }
                 for (uint64_t i = 0; i < len; i++) {  // sufr_builder.rs:149-156
-                    uint8_t c = args->text[p + i];
+                    uint8_t c = dst[i];
                     if (c >= 97 && c <= 122) c = args->ignore_softmask ? (uint8_t)'N' : (uint8_t)(c & 0x5F);
                     dst[i] = c;
                 }

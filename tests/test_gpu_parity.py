@@ -514,3 +514,27 @@ def test_sharded_fallback_on_some_ranks_only(S):
                     s.patch_seam(prev)
             assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
             assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
+
+
+def test_sharded_host_results_from_device_text(S):
+    """bench.py's multi-GPU e2e path: the text is in device memory, results go to the host, ranks > 0 carry no
+    transformed text -- the seam repair reads windows of the caller's device text."""
+    import torch
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = random.Random(41)
+    text = dna_with_rare(rng, 100000, rare=b"nacgt%", rare_p=0.02) + b"$"
+    want = O.oracle_build(text, is_dna=True, threads=4)
+    d = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    world = 3
+    shards = [S.build(S.SufrBuilderArgs(text=b"", is_dna=True), rank=r, world_size=world,
+                      device_text=(d.data_ptr(), d.numel())) for r in range(world)]
+    meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+    offs, total = shard_layout(meta)
+    for r, s in enumerate(shards):
+        s.set_shard_layout(offs[r], total)
+        prev = previous_last_suffix(meta, r)
+        if prev is not None and s.num_suffixes:
+            s.patch_seam(prev)
+    assert shards[0].text == want.text
+    assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
+    assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
