@@ -18,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sufr_b200.h"
@@ -124,6 +125,20 @@ struct EventTimer {
 // Thrown when prefix doubling is needed but this attempt sorts only a subset of the positions (suffix
 // filter applied up front, or one key-range shard): the build is redone over all positions.
 struct NeedFullSort {};
+
+// Host side of the compact device->host transfer: widen a staged array into the result with a few threads.
+template <typename Src, typename Dst>
+static void host_widen(const Src* src, Dst* dst, uint64_t count, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) {
+        pool.emplace_back([=]() {
+            uint64_t lo = count * (uint64_t)t / threads, hi = count * (uint64_t)(t + 1) / threads;
+            for (uint64_t i = lo; i < hi; i++) dst[i] = (Dst)src[i];
+        });
+    }
+    for (auto& th : pool) th.join();
+}
 
 // ---------------------------------------------------------------------------------------------
 class Build {
@@ -978,7 +993,38 @@ void Build::run(SufrB200Result* out) {
     DevBuf<unsigned long long> sa64, lcp64;
     void* d_sa_out = d_sa.get();
     void* d_lcp_out = d_lcp.get();
-    if (index_bits_ == 64) {
+    // Host results of large builds travel compactly (LCP as bytes + exceptions, 64-bit SA as u32) and are
+    // widened by host threads while the next copy is in flight: PCIe, not the GPU, bounds the end-to-end time.
+    uint64_t compact_min = 1u << 22;
+    if (const char* dbg = getenv("SUFR_B200_DEBUG_COMPACT_MIN")) compact_min = strtoull(dbg, nullptr, 10);
+    bool compact = result_memory_ == SUFR_B200_MEM_HOST && s >= compact_min && s > 0 &&
+                   !getenv("SUFR_B200_DEBUG_NO_COMPACT_D2H");
+    DevBuf<uint8_t> d_lcp8;
+    DevBuf<uint32_t> d_exc_idx, d_exc_val;
+    uint64_t exc_count = 0;
+    if (compact) {
+        const uint64_t capacity = s / 64 + 1024;
+        d_lcp8 = dalloc<uint8_t>(s + 16);
+        d_exc_idx = dalloc<uint32_t>(capacity);
+        d_exc_val = dalloc<uint32_t>(capacity);
+        auto d_cnt = dalloc<unsigned long long>(1);
+        SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
+        lcp_to_u8_kernel<<<grid_for(s, 16), kBlock, 0, st()>>>(d_lcp.get(), s, d_lcp8.get(), d_exc_idx.get(),
+                                                              d_exc_val.get(), d_cnt.get(), capacity);
+        SUFR_KERNEL_CHECK();
+        launched();
+        unsigned long long c = 0;
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&c, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st()));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+        exc_count = c;
+        if (c > capacity) {  // repetitive text: most LCP values do not fit a byte
+            compact = false;
+            d_lcp8.reset();
+            d_exc_idx.reset();
+            d_exc_val.reset();
+        }
+    }
+    if (index_bits_ == 64 && !compact) {
         sa64 = dalloc<unsigned long long>(s);
         lcp64 = dalloc<unsigned long long>(s);
         if (s) {
@@ -1029,10 +1075,50 @@ void Build::run(SufrB200Result* out) {
         owner->sa = ctx.pinned.get(s * w);
         owner->lcp = ctx.pinned.get(s * w);
         int e1 = timer.mark();
-        if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
-        if (s) {
-            SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa_out, s * w, cudaMemcpyDeviceToHost, st()));
-            SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->lcp, d_lcp_out, s * w, cudaMemcpyDeviceToHost, st()));
+        if (compact) {
+            int hw = (int)std::thread::hardware_concurrency();
+            int threads = std::max(2, std::min(16, hw / std::max(1, (int)args.world_size)));
+            // 1. LCP bytes + exceptions, widened on the host while the suffix array is in flight
+            uint8_t* h8 = (uint8_t*)ctx.pinned.get(s);
+            std::vector<uint32_t> eidx(exc_count), eval(exc_count);
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(h8, d_lcp8.get(), s, cudaMemcpyDeviceToHost, st()));
+            if (exc_count) {
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(eidx.data(), d_exc_idx.get(), exc_count * 4, cudaMemcpyDeviceToHost, st()));
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(eval.data(), d_exc_val.get(), exc_count * 4, cudaMemcpyDeviceToHost, st()));
+            }
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            void* lcp_out = owner->lcp;
+            const uint32_t bits = index_bits_;
+            std::thread lcp_worker([=, &eidx, &eval]() {
+                if (bits == 64) host_widen(h8, (uint64_t*)lcp_out, s, threads);
+                else host_widen(h8, (uint32_t*)lcp_out, s, threads);
+                for (uint64_t e = 0; e < exc_count; e++) {
+                    if (bits == 64) ((uint64_t*)lcp_out)[eidx[e]] = eval[e];
+                    else ((uint32_t*)lcp_out)[eidx[e]] = eval[e];
+                }
+            });
+            // 2. suffix array (u32 on the wire) and text
+            uint32_t* h32 = nullptr;
+            if (index_bits_ == 64) {
+                h32 = (uint32_t*)ctx.pinned.get(s * 4);
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(h32, d_sa.get(), s * 4, cudaMemcpyDeviceToHost, st()));
+            } else {
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa.get(), s * 4, cudaMemcpyDeviceToHost, st()));
+            }
+            if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            lcp_worker.join();
+            if (h32) {
+                host_widen(h32, (uint64_t*)owner->sa, s, threads);
+                ctx.pinned.put(h32);
+            }
+            ctx.pinned.put(h8);
+        } else {
+            if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
+            if (s) {
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa_out, s * w, cudaMemcpyDeviceToHost, st()));
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->lcp, d_lcp_out, s * w, cudaMemcpyDeviceToHost, st()));
+            }
         }
         int e2 = timer.mark();
         SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));

@@ -1287,6 +1287,48 @@ __global__ void __launch_bounds__(kBlock) gather_u32_kernel(uint64_t m, const ui
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) dst[a] = src[idx[a]];
 }
 
+// Compact device->host transfer of the LCP array: almost every value of a non-repetitive text fits a byte.
+// out8[j] = min(lcp[j], 255); values >= 255 are also appended to an exception list (index, value).
+__global__ void __launch_bounds__(kBlock) lcp_to_u8_kernel(const uint32_t* __restrict__ lcp, uint64_t s,
+                                                           uint8_t* __restrict__ out8, uint32_t* __restrict__ exc_idx,
+                                                           uint32_t* __restrict__ exc_val,
+                                                           unsigned long long* __restrict__ exc_count, uint64_t capacity) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 16;
+    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; j0 < s; j0 += stride) {
+        uint32_t v[16];
+        if (j0 + 15 < s) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 x = *reinterpret_cast<const uint4*>(lcp + j0 + 4 * q);
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = j0 + u < s ? lcp[j0 + u] : 0u;
+        }
+        uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            uint32_t b = v[u] < 255u ? v[u] : 255u;
+            packed[u >> 2] |= b << (8 * (u & 3));
+            if (v[u] >= 255u && j0 + u < s) {
+                unsigned long long e = atomicAdd(exc_count, 1ull);
+                if (e < capacity) {
+                    exc_idx[e] = (uint32_t)(j0 + u);
+                    exc_val[e] = v[u];
+                }
+            }
+        }
+        if (j0 + 15 < s) {
+            *reinterpret_cast<uint4*>(out8 + j0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (j0 + u < s) out8[j0 + u] = (uint8_t)(packed[u >> 2] >> (8 * (u & 3)));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) widen_kernel(uint64_t m, const uint32_t* __restrict__ src,
                                                        unsigned long long* __restrict__ dst) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

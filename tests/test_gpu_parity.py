@@ -538,3 +538,17 @@ def test_sharded_host_results_from_device_text(S):
     assert shards[0].text == want.text
     assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
     assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_compact_host_transfer(S, bits, monkeypatch):
+    """Large host results travel as LCP bytes + exceptions (and u32 SA for u64 output) and are widened on the
+    host; forced on for a small input here, with LCP values on both sides of the byte limit."""
+    monkeypatch.setenv("SUFR_B200_DEBUG_COMPACT_MIN", "1")
+    rng = random.Random(43)
+    base = dna_with_rare(rng, 60000, rare=b"N", rare_p=0.002)
+    text = base + base[1000:1400] + base[5000:5254] + base[9000:9256] + b"$"   # LCPs of 400, 254, 256
+    gpu_vs_oracle(S, text, index_bits=bits, is_dna=True)
+    gpu_vs_oracle(S, text, index_bits=bits)
+    # a text whose LCP values mostly exceed a byte falls back to the plain transfer
+    gpu_vs_oracle(S, b"ACGT" * 3000 + b"$", index_bits=bits, is_dna=True)
