@@ -127,14 +127,62 @@ struct EventTimer {
 struct NeedFullSort {};
 
 // Host side of the compact device->host transfer: widen a staged array into the result with a few threads.
+// The destination is written once and not read back, so the AVX2 path uses streaming (non-temporal) stores:
+// no read-for-ownership traffic on the host memory bus, which the incoming DMA writes share.
+}  // namespace sufr
+#include <immintrin.h>
+namespace sufr {
+
+template <typename Src, typename Dst>
+static void widen_range_scalar(const Src* src, Dst* dst, uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) dst[i] = (Dst)src[i];
+}
+__attribute__((target("avx2"))) static void widen_range_avx2(const uint8_t* src, uint64_t* dst, uint64_t lo, uint64_t hi) {
+    uint64_t i = lo;
+    for (; i < hi && ((uintptr_t)(dst + i) & 31); i++) dst[i] = src[i];
+    for (; i + 16 <= hi; i += 16) {
+        __m128i b = _mm_loadu_si128((const __m128i*)(src + i));
+        _mm256_stream_si256((__m256i*)(dst + i), _mm256_cvtepu8_epi64(b));
+        _mm256_stream_si256((__m256i*)(dst + i + 4), _mm256_cvtepu8_epi64(_mm_srli_si128(b, 4)));
+        _mm256_stream_si256((__m256i*)(dst + i + 8), _mm256_cvtepu8_epi64(_mm_srli_si128(b, 8)));
+        _mm256_stream_si256((__m256i*)(dst + i + 12), _mm256_cvtepu8_epi64(_mm_srli_si128(b, 12)));
+    }
+    for (; i < hi; i++) dst[i] = src[i];
+    _mm_sfence();
+}
+__attribute__((target("avx2"))) static void widen_range_avx2(const uint8_t* src, uint32_t* dst, uint64_t lo, uint64_t hi) {
+    uint64_t i = lo;
+    for (; i < hi && ((uintptr_t)(dst + i) & 31); i++) dst[i] = src[i];
+    for (; i + 16 <= hi; i += 16) {
+        __m128i b = _mm_loadu_si128((const __m128i*)(src + i));
+        _mm256_stream_si256((__m256i*)(dst + i), _mm256_cvtepu8_epi32(b));
+        _mm256_stream_si256((__m256i*)(dst + i + 8), _mm256_cvtepu8_epi32(_mm_srli_si128(b, 8)));
+    }
+    for (; i < hi; i++) dst[i] = src[i];
+    _mm_sfence();
+}
+__attribute__((target("avx2"))) static void widen_range_avx2(const uint32_t* src, uint64_t* dst, uint64_t lo, uint64_t hi) {
+    uint64_t i = lo;
+    for (; i < hi && ((uintptr_t)(dst + i) & 31); i++) dst[i] = src[i];
+    for (; i + 8 <= hi; i += 8) {
+        __m256i a = _mm256_loadu_si256((const __m256i*)(src + i));
+        _mm256_stream_si256((__m256i*)(dst + i), _mm256_cvtepu32_epi64(_mm256_castsi256_si128(a)));
+        _mm256_stream_si256((__m256i*)(dst + i + 4), _mm256_cvtepu32_epi64(_mm256_extracti128_si256(a, 1)));
+    }
+    for (; i < hi; i++) dst[i] = src[i];
+    _mm_sfence();
+}
+
 template <typename Src, typename Dst>
 static void host_widen(const Src* src, Dst* dst, uint64_t count, int threads) {
     if (threads < 1) threads = 1;
+    static const bool avx2 = __builtin_cpu_supports("avx2");
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++) {
         pool.emplace_back([=]() {
             uint64_t lo = count * (uint64_t)t / threads, hi = count * (uint64_t)(t + 1) / threads;
-            for (uint64_t i = lo; i < hi; i++) dst[i] = (Dst)src[i];
+            if (avx2) widen_range_avx2(src, dst, lo, hi);
+            else widen_range_scalar(src, dst, lo, hi);
         });
     }
     for (auto& th : pool) th.join();
@@ -1077,7 +1125,7 @@ void Build::run(SufrB200Result* out) {
         int e1 = timer.mark();
         if (compact) {
             int hw = (int)std::thread::hardware_concurrency();
-            int threads = std::max(2, std::min(16, hw / std::max(1, (int)args.world_size)));
+            int threads = std::max(2, std::min(8, hw / (2 * std::max(1, (int)args.world_size))));
             // 1. LCP bytes + exceptions, widened on the host while the suffix array is in flight
             uint8_t* h8 = (uint8_t*)ctx.pinned.get(s);
             std::vector<uint32_t> eidx(exc_count), eval(exc_count);
@@ -1097,21 +1145,31 @@ void Build::run(SufrB200Result* out) {
                     else ((uint32_t*)lcp_out)[eidx[e]] = eval[e];
                 }
             });
-            // 2. suffix array (u32 on the wire) and text
-            uint32_t* h32 = nullptr;
+            // 2. text and suffix array (u32 on the wire, in chunks that are widened while the next ones arrive)
+            if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
             if (index_bits_ == 64) {
-                h32 = (uint32_t*)ctx.pinned.get(s * 4);
-                SUFR_CUDA_CHECK(cudaMemcpyAsync(h32, d_sa.get(), s * 4, cudaMemcpyDeviceToHost, st()));
+                uint32_t* h32 = (uint32_t*)ctx.pinned.get(s * 4);
+                constexpr int kChunks = 8;
+                cudaEvent_t done[kChunks];
+                for (int c = 0; c < kChunks; c++) {
+                    uint64_t lo = s * (uint64_t)c / kChunks, hi = s * (uint64_t)(c + 1) / kChunks;
+                    if (hi > lo)
+                        SUFR_CUDA_CHECK(cudaMemcpyAsync(h32 + lo, d_sa.get() + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, st()));
+                    SUFR_CUDA_CHECK(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+                    SUFR_CUDA_CHECK(cudaEventRecord(done[c], st()));
+                }
+                for (int c = 0; c < kChunks; c++) {
+                    uint64_t lo = s * (uint64_t)c / kChunks, hi = s * (uint64_t)(c + 1) / kChunks;
+                    SUFR_CUDA_CHECK(cudaEventSynchronize(done[c]));
+                    cudaEventDestroy(done[c]);
+                    if (hi > lo) host_widen(h32 + lo, (uint64_t*)owner->sa + lo, hi - lo, threads);
+                }
+                ctx.pinned.put(h32);
             } else {
                 SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa.get(), s * 4, cudaMemcpyDeviceToHost, st()));
             }
-            if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
             lcp_worker.join();
-            if (h32) {
-                host_widen(h32, (uint64_t*)owner->sa, s, threads);
-                ctx.pinned.put(h32);
-            }
             ctx.pinned.put(h8);
         } else {
             if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
