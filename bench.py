@@ -411,10 +411,14 @@ def run_e2e(args, S, ctx, d_text, text_len, bargs, rank, world, dev, barrier):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    h2d = 0
+    out_bytes = 0
     tot = 0
     for _ in range(args.e2e_steps):
         r = step()
-        d2h = (r.text_len if rank == 0 else 0) + 2 * r.num_suffixes * (args.index_bits // 8)
+        d2h = r.d2h_bytes                      # bytes that crossed PCIe (compact encoding, see sufr_b200.h)
+        h2d = r.h2d_bytes if world == 1 else (text_len if rank == 0 else 0)
+        out_bytes = (r.text_len if rank == 0 else 0) + 2 * r.num_suffixes * (args.index_bits // 8)
         tot = r.total_suffixes
         _ = int(r.sa[:1024].sum()) if r.num_suffixes else 0  # read the step's result on the host
         r.free()
@@ -425,9 +429,10 @@ def run_e2e(args, S, ctx, d_text, text_len, bargs, rank, world, dev, barrier):
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed = float(el.item())
     return {"value": tot * args.e2e_steps / elapsed, "unit": "suffixes/s",
-            "h2d_bytes_per_step": text_len if rank == 0 else 0, "d2h_bytes_per_step": d2h,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_result_bytes_per_step": out_bytes,
             "ms_per_step": 1e3 * elapsed / args.e2e_steps, "steps": args.e2e_steps,
-            "note": "pinned host text -> H2D -> build -> D2H of text+SA+LCP into pinned host buffers, per step"}
+            "note": "pinned host text -> H2D -> build -> D2H (LCP as bytes + exceptions, u64 SA as u32, widened by host "
+                    "threads into the pinned u64 result arrays), per step; bytes are those of rank 0"}
 
 
 def _with_text(bargs, h_text):

@@ -106,6 +106,9 @@ typedef struct SufrB200Result {
     uint32_t bits_per_symbol;
     uint32_t refine_rounds;   /* next-word refinement rounds */
     uint32_t doubling_rounds; /* prefix-doubling rounds (0 unless the text has deep repeats) */
+    uint64_t h2d_bytes;       /* bytes this build copied host -> device (0 for a device-resident text) */
+    uint64_t d2h_bytes;       /* bytes it copied device -> host: large host results travel compactly (LCP as */
+                              /*   bytes + exceptions, 64-bit SA as u32) and are widened by host threads */
     void* owner;              /* internal */
 } SufrB200Result;
 

@@ -81,6 +81,8 @@ class Result(C.Structure):
         ("bits_per_symbol", C.c_uint32),
         ("refine_rounds", C.c_uint32),
         ("doubling_rounds", C.c_uint32),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
         ("owner", C.c_void_p),
     ]
 

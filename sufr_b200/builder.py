@@ -210,6 +210,10 @@ class BuildResult:
     @property
     def kernel_launches(self): return int(self.c.kernel_launches)
     @property
+    def h2d_bytes(self): return int(self.c.h2d_bytes)
+    @property
+    def d2h_bytes(self): return int(self.c.d2h_bytes)
+    @property
     def n_ranges(self) -> List[Tuple[int, int]]:
         return [(int(self.c.n_ranges[2 * i]), int(self.c.n_ranges[2 * i + 1])) for i in range(self.c.num_n_ranges)]
 

@@ -222,6 +222,7 @@ class Build {
     bool sentinel_ = false;             // filtered suffixes ride through the sort with key ~0
     uint64_t sort_n_ = 0;               // elements handed to the main sort (>= s when sentinel_)
     uint64_t indexed_count_ = 0;        // bytes in ACGT$ (counted by the transform kernel)
+    uint64_t h2d_bytes_ = 0, d2h_bytes_ = 0;
     DevBuf<uint64_t> d_nstarts, d_nends;
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
@@ -950,6 +951,7 @@ void Build::run(SufrB200Result* out) {
         d_raw_owned = dalloc<uint8_t>(n + 16);
         int e0 = timer.mark();
         if (n) SUFR_CUDA_CHECK(cudaMemcpyAsync(d_raw_owned.get(), args.text, n, cudaMemcpyHostToDevice, st()));
+        h2d_bytes_ += n;
         int e1 = timer.mark();
         SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
         tm.h2d_ms = timer.ms(e0, e1);
@@ -1127,6 +1129,7 @@ void Build::run(SufrB200Result* out) {
             int hw = (int)std::thread::hardware_concurrency();
             int threads = std::max(2, std::min(8, hw / (2 * std::max(1, (int)args.world_size))));
             // 1. LCP bytes + exceptions, widened on the host while the suffix array is in flight
+            d2h_bytes_ += s + exc_count * 8 + s * 4 + (want_text ? n : 0);
             uint8_t* h8 = (uint8_t*)ctx.pinned.get(s);
             std::vector<uint32_t> eidx(exc_count), eval(exc_count);
             SUFR_CUDA_CHECK(cudaMemcpyAsync(h8, d_lcp8.get(), s, cudaMemcpyDeviceToHost, st()));
@@ -1145,6 +1148,10 @@ void Build::run(SufrB200Result* out) {
                     else ((uint32_t*)lcp_out)[eidx[e]] = eval[e];
                 }
             });
+            struct Joiner {  // a CUDA error below must not leave the worker running on freed buffers
+                std::thread& t;
+                ~Joiner() { if (t.joinable()) t.join(); }
+            } joiner{lcp_worker};
             // 2. text and suffix array (u32 on the wire, in chunks that are widened while the next ones arrive)
             if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
             if (index_bits_ == 64) {
@@ -1172,6 +1179,7 @@ void Build::run(SufrB200Result* out) {
             lcp_worker.join();
             ctx.pinned.put(h8);
         } else {
+            d2h_bytes_ += 2 * s * w + (want_text ? n : 0);
             if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
             if (s) {
                 SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa_out, s * w, cudaMemcpyDeviceToHost, st()));
@@ -1209,6 +1217,8 @@ void Build::run(SufrB200Result* out) {
     out->bits_per_symbol = ks.pt.bits;
     out->refine_rounds = refine_rounds;
     out->doubling_rounds = doubling_rounds;
+    out->h2d_bytes = h2d_bytes_;
+    out->d2h_bytes = d2h_bytes_;
     out->owner = owner.release();
 }
 
