@@ -373,6 +373,9 @@ void Build::encode(const uint8_t* d_raw) {
             launched();
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
             ks.fast2 = 1;
+            ks.reg_indexed = 1;
+            for (int k = 0; k < 4; k++)
+                if (!strchr("ACGT$", reg[k]) || reg[k] == 0) ks.reg_indexed = 0;
             ks.packed2_words = words2 + 2;
             ks.irr_words = words2 / 2 + 2;
             ks.packed2 = d_packed2.get();
@@ -532,8 +535,12 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             pos_a = dalloc<uint32_t>(capacity);
             SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
             if (n) {
-                select_append_kernel<<<grid_for(n, 32), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
-                                                                         pos_a.get(), d_cnt.get(), capacity);
+                if (ks.fast2 && !getenv("SUFR_B200_DEBUG_OLD_SELECT"))
+                    select_fast2_kernel<<<grid_for(n, 32), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
+                                                                            pos_a.get(), d_cnt.get(), capacity);
+                else
+                    select_append_kernel<<<grid_for(n, 32), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
+                                                                             pos_a.get(), d_cnt.get(), capacity);
                 SUFR_KERNEL_CHECK();
                 launched();
             }

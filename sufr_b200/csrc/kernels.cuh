@@ -342,6 +342,102 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
     }
 }
 
+// Fast-path variant of select_append_kernel.  A warp owns 1024 consecutive positions and lane l the 32 positions
+// of packed2 word l, so a key is two funnel shifts of registers the lane already holds (no per-row shuffles or
+// ballots).  Phase 1 leaves a 32-bit take mask per lane; phase 2 enumerates the taken positions densely (prefix
+// sums over the lanes, k-th set bit of the owner's mask) so that the records leave the warp as coalesced stores.
+__device__ __forceinline__ uint32_t select_bit(uint32_t m, uint32_t k) {  // position of the k-th (0-based) set bit
+    uint32_t pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
+    c = m & 1u;              if (k >= c) pos += 1;
+    return pos;
+}
+__global__ void __launch_bounds__(kBlock) select_fast2_kernel(KeySpec ks, uint64_t n, uint64_t lo, uint64_t hi,
+                                                              int filter, uint64_t* __restrict__ keys,
+                                                              uint32_t* __restrict__ pos,
+                                                              unsigned long long* __restrict__ count,
+                                                              uint64_t capacity) {
+    constexpr int WARPS = kBlock / 32;
+    constexpr uint64_t kWin = ~0ull << (64 - kFast2Symbols);
+    __shared__ uint32_t incl_s[WARPS][32];
+    __shared__ uint32_t wbase[WARPS];
+    __shared__ unsigned long long gbase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)WARPS * 1024;
+    const uint64_t chunks = (n + chunk - 1) / chunk;
+    for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+        const uint64_t W0 = c * chunk + (uint64_t)warp * 1024;
+        const uint64_t q = (W0 >> 5) + lane;
+        const uint64_t w = q < ks.packed2_words ? __ldg(ks.packed2 + q) : 0ull;
+        uint64_t wn = __shfl_down_sync(0xffffffffu, w, 1);
+        if (lane == 31) wn = q + 1 < ks.packed2_words ? __ldg(ks.packed2 + q + 1) : 0ull;
+        const uint64_t qi = (W0 >> 6) + lane;
+        const uint64_t ir = (lane <= 16 && qi < ks.irr_words) ? __ldg(ks.irr + qi) : ~0ull;
+        const uint64_t i0 = __shfl_sync(0xffffffffu, ir, lane >> 1);
+        const uint64_t i1 = __shfl_sync(0xffffffffu, ir, (lane >> 1) + 1);
+        const uint64_t M = (lane & 1) ? ((i0 << 32) | (i1 >> 32)) : i0;  // irregular bits of positions P0 .. P0+63
+        const uint64_t P0 = W0 + 32u * lane;
+        uint32_t T = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            uint64_t key = (j ? ((w << (2 * j)) | (wn >> ((64 - 2 * j) & 63))) : w) & ~3ull;
+            const uint64_t m = (M << j) & kWin;
+            const uint64_t p = P0 + j;
+            if (m) key = p < n ? first_key_fast2_slow(ks, p) : 0ull;
+            bool take = p < n && key >= lo && (hi == 0 || key < hi);
+            if (take && filter && (!ks.reg_indexed || (m >> 63))) take = indexed_byte(ks.text[p]);
+            T |= (take ? 1u : 0u) << j;
+        }
+        // dense enumeration of the taken positions
+        uint32_t incl = __popc(T);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        incl_s[warp][lane] = incl;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) wbase[warp] = total;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int k = 0; k < WARPS; k++) { uint32_t t = wbase[k]; wbase[k] = acc; acc += t; }
+            gbase = acc ? atomicAdd(count, (unsigned long long)acc) : 0ull;
+        }
+        __syncthreads();
+        const unsigned long long base = gbase + wbase[warp];
+        for (uint32_t s0 = 0; s0 < total; s0 += 32) {
+            const uint32_t sidx = s0 + lane;
+            const bool act = sidx < total;
+            uint32_t l = 0;
+            if (act) {
+#pragma unroll
+                for (int step = 16; step; step >>= 1)
+                    if (incl_s[warp][l + step - 1] <= sidx) l += step;
+            }
+            const uint32_t Tl = __shfl_sync(0xffffffffu, T, l);
+            const uint64_t wl = __shfl_sync(0xffffffffu, w, l);
+            const uint64_t wnl = __shfl_sync(0xffffffffu, wn, l);
+            const uint64_t Ml = __shfl_sync(0xffffffffu, M, l);
+            if (act) {
+                const uint32_t j = select_bit(Tl, sidx - (incl_s[warp][l] - __popc(Tl)));
+                const uint64_t p = W0 + 32u * l + j;
+                uint64_t key = (j ? ((wl << (2 * j)) | (wnl >> (64 - 2 * j))) : wl) & ~3ull;
+                if ((Ml << j) & kWin) key = first_key_fast2_slow(ks, p);
+                const unsigned long long idx = base + sidx;
+                if (idx < capacity) {
+                    keys[idx] = key;
+                    pos[idx] = (uint32_t)p;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Histogram of the top `hbits` bits of the first key word over the indexed suffixes (splitter selection).
 // With sample_shift > 0 only every 2^sample_shift-th position is counted (enough to balance the shards).
 __global__ void __launch_bounds__(kBlock) key_hist_kernel(KeySpec ks, uint64_t n, uint32_t hbits,

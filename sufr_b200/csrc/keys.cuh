@@ -42,6 +42,7 @@ struct KeySpec {
     const uint8_t* cls;        // [256] byte -> number of regular bytes smaller than it (0..4); regular bytes: their rank
     uint64_t packed2_words;    // allocation sizes (bounds of the warp-window loads)
     uint64_t irr_words;
+    int reg_indexed;           // every regular byte is one of ACGT$: only irregular positions can be filtered out
 };
 
 // Fast-path keys: bit 0 = the key contains fill (an irregular symbol inside its 31-symbol window),
@@ -144,6 +145,8 @@ __device__ __forceinline__ uint64_t first_key_fast2(const KeySpec& ks, uint64_t 
 }
 
 __device__ __forceinline__ uint64_t first_key(const KeySpec& ks, uint64_t p);
+// out-of-line copy for the rare irregular windows inside unrolled loops
+__device__ __noinline__ uint64_t first_key_fast2_slow(const KeySpec& ks, uint64_t p) { return first_key_fast2(ks, p); }
 
 // Warp-cooperative key generation on the fast path: a warp owns 1024 consecutive positions starting at W0
 // (a multiple of 1024).  Lane l holds packed2 word W0/32 + l and (l <= 16) irr word W0/64 + l; the key of
