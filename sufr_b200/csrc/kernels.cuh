@@ -41,7 +41,24 @@ inline uint32_t grid_for(uint64_t n, int per_thread = 1) {
 }
 
 // ------------------------------------------------------------------ encode (sufr_builder.rs:144-160)
-// Lowercase ASCII -> 'N' (ignore_softmask) or uppercase; also records which bytes occur.
+// Lowercase ASCII -> 'N' (ignore_softmask) or uppercase; also records which bytes occur.  Four bytes at a time:
+// 0x80 in every byte of w that equals the byte replicated in pat
+__device__ __forceinline__ uint32_t swar_eq(uint32_t w, uint32_t pat) {
+    uint32_t v = w ^ pat;
+    return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t transform_word(uint32_t w, int ignore_softmask) {
+    uint32_t x = w & 0x7F7F7F7Fu;
+    uint32_t ge97 = x + 0x1F1F1F1Fu;   // bit 7 of a byte: x >= 97
+    uint32_t ge123 = x + 0x05050505u;  // bit 7 of a byte: x >= 123
+    uint32_t lower = ge97 & ~ge123 & ~w & 0x80808080u;
+    uint32_t lm = (lower >> 7) * 0xFFu;
+    return ignore_softmask ? ((w & ~lm) | (0x4E4E4E4Eu & lm)) : (w & ~(lm & 0x20202020u));
+}
+__device__ __forceinline__ uint32_t transform_byte(uint32_t c, int ignore_softmask) {
+    if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
+    return c;
+}
 __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __restrict__ in,
                                                            uint8_t* __restrict__ out, uint64_t n,
                                                            int ignore_softmask, uint32_t* __restrict__ present,
@@ -52,33 +69,46 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
     seen[threadIdx.x] = 0;
     cnt[threadIdx.x] = 0;
     unsigned long long nidx = 0;   // bytes that start an indexed suffix under --dna (sufr_builder.rs:446-449)
+    uint32_t acc_a = 0, acc_c = 0, acc_g = 0, acc_t = 0;
     __syncthreads();
     const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const uint64_t nvec = aligned ? n / 16 : 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    uint32_t iter = 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride, iter++) {
         uint4 x = reinterpret_cast<const uint4*>(in)[v];
         uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            uint32_t r = 0;
+            const uint32_t t = transform_word(w[k], ignore_softmask);
+            const uint32_t ea = swar_eq(t, 0x41414141u), ec = swar_eq(t, 0x43434343u);
+            const uint32_t eg = swar_eq(t, 0x47474747u), et = swar_eq(t, 0x54545454u);
+            const uint32_t acgt = ea | ec | eg | et;
+            acc_a |= ea; acc_c |= ec; acc_g |= eg; acc_t |= et;
+            nidx += __popc(acgt | swar_eq(t, 0x24242424u));
+            if (acgt != 0x80808080u) {  // other bytes (rare in DNA): per-byte presence
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                uint32_t c = (w[k] >> (8 * b)) & 0xFF;
-                if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
-                seen[c] = 1;
-                if ((v & 63) == 0) atomicAdd(&cnt[c], 1u);
-                nidx += (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '$') ? 1 : 0;
-                r |= c << (8 * b);
+                for (int b = 0; b < 4; b++)
+                    if (!((acgt >> (8 * b + 7)) & 1u)) seen[(t >> (8 * b)) & 0xFFu] = 1;
             }
-            w[k] = r;
+            w[k] = t;
+        }
+        if ((iter & 63u) == 0) {  // block-uniform: one grid-stride sweep in 64 is the sample
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) atomicAdd(&cnt[(w[k] >> (8 * b)) & 0xFFu], 1u);
         }
         reinterpret_cast<uint4*>(out)[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if (acc_a) seen['A'] = 1;
+    if (acc_c) seen['C'] = 1;
+    if (acc_g) seen['G'] = 1;
+    if (acc_t) seen['T'] = 1;
     for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t c = in[i];
-        if (c >= 97 && c <= 122) c = ignore_softmask ? (uint32_t)'N' : (c & 0x5F);
+        uint32_t c = transform_byte(in[i], ignore_softmask);
         seen[c] = 1;
+        if (nvec == 0) atomicAdd(&cnt[c], 1u);  // unaligned / tiny inputs: the tail is the whole text
         nidx += (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '$') ? 1 : 0;
         out[i] = (uint8_t)c;
     }
@@ -127,17 +157,19 @@ __global__ void __launch_bounds__(kBlock) pack2_kernel(const uint8_t* __restrict
 }
 
 // One 64-bit word (K symbols) per thread.  The block's 256*K text bytes are staged in shared memory with
-// 16-byte loads (the text buffer is padded by 16 bytes); `text` must be 16-byte aligned.
+// 16-byte loads (the text buffer is padded by 16 bytes); `text` must be 16-byte aligned.  For K <= 24 a thread
+// reads its K bytes as seven 32-bit words and realigns them with funnel shifts (byte-wise shared-memory reads
+// at a stride of K bytes are 5-way bank conflicts).
 __global__ void __launch_bounds__(kBlock) pack_kernel(const uint8_t* __restrict__ text, uint64_t n,
                                                       const uint8_t* __restrict__ code_lut, uint32_t bits,
                                                       uint32_t K, uint64_t num_words, uint64_t* __restrict__ words) {
     __shared__ uint8_t lut[256];
-    __shared__ __align__(16) uint8_t raw[kBlock * 64];
+    __shared__ __align__(16) uint8_t raw[kBlock * 64 + 32];
     lut[threadIdx.x] = code_lut[threadIdx.x];
     const uint64_t blocks = (num_words + kBlock - 1) / kBlock;
     for (uint64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
         const uint64_t byte0 = b * kBlock * K;
-        const uint32_t nvec = (kBlock * K + 15) / 16;
+        const uint32_t nvec = (kBlock * K + 15) / 16 + 2;
         __syncthreads();
         for (uint32_t v = threadIdx.x; v < nvec; v += kBlock) {
             uint64_t off = byte0 + (uint64_t)v * 16;
@@ -150,9 +182,27 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(const uint8_t* __restrict_
         if (w < num_words) {
             const uint64_t base = w * K;
             uint64_t x = 0;
-            for (uint32_t j = 0; j < K; j++) {
-                uint64_t c = base + j < n ? lut[raw[threadIdx.x * K + j]] : 0;
-                x |= c << (64 - bits * (j + 1));
+            if (K <= 24) {
+                const uint32_t b0 = threadIdx.x * K;
+                const uint32_t* r32 = reinterpret_cast<const uint32_t*>(raw) + (b0 >> 2);
+                const uint32_t sh = 8 * (b0 & 3);
+                uint32_t r[7], a[6];
+#pragma unroll
+                for (int i = 0; i < 7; i++) r[i] = r32[i];
+#pragma unroll
+                for (int i = 0; i < 6; i++) a[i] = __funnelshift_r(r[i], r[i + 1], sh);
+#pragma unroll
+                for (uint32_t j = 0; j < 24; j++) {
+                    if (j < K) {
+                        uint64_t c = base + j < n ? lut[(a[j >> 2] >> (8 * (j & 3))) & 0xFFu] : 0;
+                        x |= c << (64 - bits * (j + 1));
+                    }
+                }
+            } else {
+                for (uint32_t j = 0; j < K; j++) {
+                    uint64_t c = base + j < n ? lut[raw[threadIdx.x * K + j]] : 0;
+                    x |= c << (64 - bits * (j + 1));
+                }
             }
             words[w] = x;
         }

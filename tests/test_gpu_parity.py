@@ -116,6 +116,10 @@ ALPHABETS = {
     "protein": (b"ACDEFGHIKLMNPQRSTVWY%", dict()),
     "binary": (b"AB", dict()),
     "bytes": (bytes(range(1, 36)) + bytes(range(128, 250)), dict()),
+    # both sides of the lowercase range 97..122, and the same bytes with bit 7 set (4-bytes-at-a-time transform)
+    "case_edges": (bytes([0x40, 0x41, 0x5A, 0x5B, 0x60, 0x61, 0x6E, 0x7A, 0x7B, 0x7F, 0x80, 0xC1, 0xE1, 0xFA, 0xFF]), dict()),
+    "case_edges_soft": (bytes([0x40, 0x41, 0x5A, 0x5B, 0x60, 0x61, 0x6E, 0x7A, 0x7B, 0x7F, 0x80, 0xC1, 0xE1, 0xFA, 0xFF]),
+                        dict(ignore_softmask=True)),
 }
 
 
