@@ -325,12 +325,6 @@ void Build::encode(const uint8_t* d_raw) {
     SUFR_CUDA_CHECK(cudaMemsetAsync(d_words.get() + num_words, 0, 2 * sizeof(uint64_t), st()));
     auto d_lut = dalloc<uint8_t>(256);
     SUFR_CUDA_CHECK(cudaMemcpyAsync(d_lut.get(), lut, 256, cudaMemcpyHostToDevice, st()));
-    if (num_words) {
-        pack_kernel<<<grid_for(num_words), kBlock, 0, st()>>>(d_text.get(), n, d_lut.get(), bits, pt.K, num_words,
-                                                             d_words.get());
-        SUFR_KERNEL_CHECK();
-        launched();
-    }
     pt.words = d_words.get();
     ks.text = d_text.get();
 
@@ -338,6 +332,8 @@ void Build::encode(const uint8_t* d_raw) {
     // most frequent bytes of a 1/64 sample are the "regular" symbols; any choice is correct, it only decides
     // how many keys contain fill.
     ks.fast2 = 0;
+    DevBuf<uint8_t> d_cls2;
+    uint64_t words2 = 0;
     if (ks.mode == kModeFull && n >= 4096 && !getenv("SUFR_B200_DEBUG_NO_FAST2")) {
         int order[256];
         for (int b = 0; b < 256; b++) order[b] = b;
@@ -358,20 +354,15 @@ void Build::encode(const uint8_t* d_raw) {
                 cls[b] = (uint8_t)(rank >= 0 ? rank : c);
                 cls2[b] = (uint8_t)(rank >= 0 ? rank : ((c > 3 ? 3 : c) | 4));
             }
-            uint64_t words2 = (div_up(n, 32) + 3) & ~1ull;  // even, with padding words generated by the kernel
+            words2 = (div_up(n, 32) + 3) & ~1ull;  // even, with padding words generated by the kernel
             d_packed2 = dalloc<uint64_t>(words2 + 2);
             d_irr = dalloc<uint64_t>(words2 / 2 + 2);
             d_cls = dalloc<uint8_t>(256);
-            auto d_cls2 = dalloc<uint8_t>(256);
+            d_cls2 = dalloc<uint8_t>(256);
             SUFR_CUDA_CHECK(cudaMemcpyAsync(d_cls.get(), cls, 256, cudaMemcpyHostToDevice, st()));
             SUFR_CUDA_CHECK(cudaMemcpyAsync(d_cls2.get(), cls2, 256, cudaMemcpyHostToDevice, st()));
             SUFR_CUDA_CHECK(cudaMemsetAsync(d_packed2.get() + words2, 0, 2 * 8, st()));
             SUFR_CUDA_CHECK(cudaMemsetAsync(d_irr.get() + words2 / 2, 0xFF, 2 * 8, st()));
-            pack2_kernel<<<grid_for(words2), kBlock, 0, st()>>>(d_text.get(), n, d_cls2.get(), words2, d_packed2.get(),
-                                                               reinterpret_cast<uint32_t*>(d_irr.get()));
-            SUFR_KERNEL_CHECK();
-            launched();
-            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
             ks.fast2 = 1;
             ks.reg_indexed = 1;
             for (int k = 0; k < 4; k++)
@@ -382,6 +373,15 @@ void Build::encode(const uint8_t* d_raw) {
             ks.irr = d_irr.get();
             ks.cls = d_cls.get();
         }
+    }
+    if (num_words) {
+        // grid: a multiple of the SM count; every block walks its tiles with a two-deep cp.async pipeline
+        uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(num_words, kBlock), (uint64_t)kNumSMs * 6);
+        pack_kernel<<<grid, kBlock, 0, st()>>>(d_text.get(), n, d_lut.get(), bits, pt.K, num_words, d_words.get(),
+                                               ks.fast2 ? d_cls2.get() : nullptr, words2, d_packed2.get(),
+                                               reinterpret_cast<uint32_t*>(d_irr.get()));
+        SUFR_KERNEL_CHECK();
+        launched();
     }
     SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));  // lut / present are freed on return
 }
@@ -468,7 +468,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         // input order (mask / max-query-len) use the exact histogram, which also yields the exact shard
         // offsets.  The cut points are fixed by the FIRST histogram of a build: the full-sort fallback (which
         // only some ranks may take) re-counts exactly but keeps the same cuts.
-        const uint32_t hbits = 12, bins = 1u << hbits;
+        const uint32_t hbits = kShardHistBits, bins = 1u << hbits;
         const bool exact = ks.mode != kModeFull || cuts_ready_;
         const uint32_t sample_shift = exact ? 0 : 4;
         auto d_hist = dalloc<unsigned long long>(bins);

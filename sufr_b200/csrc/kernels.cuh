@@ -4,6 +4,8 @@
 #include "keys.cuh"
 #include "scan.cuh"
 
+#include <cuda_pipeline.h>
+
 namespace sufr {
 
 constexpr int kBlock = 256;
@@ -120,92 +122,118 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
     if (cnt[threadIdx.x]) atomicAdd(&sample_counts[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
 }
 
-// 2-bit fast path: one 64-bit word of `packed2` (32 symbols) per thread, and the matching 32 bits of `irr`.
-// cls2[b] = 2-bit code of byte b (rank of a regular byte, min(class, 3) of an irregular one) | 4 if irregular.
-__global__ void __launch_bounds__(kBlock) pack2_kernel(const uint8_t* __restrict__ text, uint64_t n,
-                                                       const uint8_t* __restrict__ cls2, uint64_t num_words,
-                                                       uint64_t* __restrict__ packed2, uint32_t* __restrict__ irr32) {
-    __shared__ uint8_t lut[256];
-    lut[threadIdx.x] = cls2[threadIdx.x];
-    __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < num_words; w += stride) {
-        uint64_t base = w * 32;
-        uint64_t x = 0;
-        uint32_t m = 0;
-        uint32_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (base < n) {  // two 16-byte loads (the text buffer is 16-byte aligned and padded by 16 bytes)
-            uint4 a = *reinterpret_cast<const uint4*>(text + base);
-            bytes[0] = a.x; bytes[1] = a.y; bytes[2] = a.z; bytes[3] = a.w;
-            if (base + 16 < n) {
-                uint4 c4 = *reinterpret_cast<const uint4*>(text + base + 16);
-                bytes[4] = c4.x; bytes[5] = c4.y; bytes[6] = c4.z; bytes[7] = c4.w;
-            }
-        }
-#pragma unroll
-        for (uint32_t j = 0; j < 32; j++) {
-            uint64_t i = base + j;
-            uint32_t byte = (bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            uint32_t c = i < n ? lut[byte] : 4u;  // beyond the text: irregular, class 0
-            x |= (uint64_t)(c & 3u) << (62 - 2 * j);
-            m |= (c >> 2) << (31 - j);
-        }
-        packed2[w] = x;
-        // irr is addressed as 64-bit words with symbol 0 in the top bit: 32-bit halves are swapped on little-endian
-        irr32[w ^ 1] = m;
-    }
-}
-
-// One 64-bit word (K symbols) per thread.  The block's 256*K text bytes are staged in shared memory with
-// 16-byte loads (the text buffer is padded by 16 bytes); `text` must be 16-byte aligned.  For K <= 24 a thread
-// reads its K bytes as seven 32-bit words and realigns them with funnel shifts (byte-wise shared-memory reads
-// at a stride of K bytes are 5-way bank conflicts).
+// Packed text, both forms in one pass over the transformed text.
+//  * `words`: one 64-bit word (K symbols of `bits` bits) per thread.  For K <= 24 a thread reads its K bytes from
+//    the staged tile as seven 32-bit words and realigns them with funnel shifts (byte-wise shared-memory reads at
+//    a stride of K bytes are 5-way bank conflicts).
+//  * `packed2` / `irr32` (2-bit fast path, optional): 32 symbols per 64-bit word and the matching 32 bits of `irr`.
+//    cls2[b] = 2-bit code of byte b (rank of a regular byte, min(class, 3) of an irregular one) | 4 if irregular.
+// A tile is the 256*K bytes of one block iteration (a multiple of 32 bytes, so packed2 words do not straddle
+// tiles); tiles are double-buffered in shared memory with 16-byte cp.async (`text` must be 16-byte aligned and
+// padded by 16 bytes), so the loads of the next tile are in flight while this one is packed.
+constexpr int kPackTile = kBlock * 64 + 32;
 __global__ void __launch_bounds__(kBlock) pack_kernel(const uint8_t* __restrict__ text, uint64_t n,
                                                       const uint8_t* __restrict__ code_lut, uint32_t bits,
-                                                      uint32_t K, uint64_t num_words, uint64_t* __restrict__ words) {
+                                                      uint32_t K, uint64_t num_words, uint64_t* __restrict__ words,
+                                                      const uint8_t* __restrict__ cls2, uint64_t num_words2,
+                                                      uint64_t* __restrict__ packed2, uint32_t* __restrict__ irr32) {
     __shared__ uint8_t lut[256];
-    __shared__ __align__(16) uint8_t raw[kBlock * 64 + 32];
+    __shared__ uint8_t lut2[256];
+    __shared__ __align__(16) uint8_t raw[2][kPackTile];
     lut[threadIdx.x] = code_lut[threadIdx.x];
+    lut2[threadIdx.x] = cls2 ? cls2[threadIdx.x] : 0;
     const uint64_t blocks = (num_words + kBlock - 1) / kBlock;
-    for (uint64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
-        const uint64_t byte0 = b * kBlock * K;
-        const uint32_t nvec = (kBlock * K + 15) / 16 + 2;
-        __syncthreads();
+    const uint32_t tile_bytes = kBlock * K;
+    const uint32_t nvec = (tile_bytes + 15) / 16 + 2;
+    auto stage = [&](int buf, uint64_t b) {
+        const uint64_t byte0 = b * tile_bytes;
         for (uint32_t v = threadIdx.x; v < nvec; v += kBlock) {
-            uint64_t off = byte0 + (uint64_t)v * 16;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (off < n) x = *reinterpret_cast<const uint4*>(text + off);  // may read the 16 padding bytes
-            reinterpret_cast<uint4*>(raw)[v] = x;
+            const uint64_t off = byte0 + (uint64_t)v * 16;
+            const bool in = off < n;  // may read the 16 padding bytes; beyond them: zero fill
+            __pipeline_memcpy_async(raw[buf] + v * 16, in ? text + off : text, 16, in ? 0 : 16);
         }
+    };
+    int buf = 0;
+    uint64_t b = blockIdx.x;
+    if (b < blocks) stage(0, b);
+    __pipeline_commit();
+    for (; b < blocks; b += gridDim.x, buf ^= 1) {
+        if (b + gridDim.x < blocks) stage(buf ^ 1, b + gridDim.x);
+        __pipeline_commit();
+        __pipeline_wait_prior(1);
         __syncthreads();
+        const uint8_t* tile = raw[buf];
+        const uint64_t byte0 = b * tile_bytes;
         const uint64_t w = b * kBlock + threadIdx.x;
         if (w < num_words) {
             const uint64_t base = w * K;
             uint64_t x = 0;
-            if (K <= 24) {
+            if (K <= 24 && base + K <= n) {
+                // Horner accumulation: one multiply-add per symbol instead of a variable 64-bit shift
                 const uint32_t b0 = threadIdx.x * K;
-                const uint32_t* r32 = reinterpret_cast<const uint32_t*>(raw) + (b0 >> 2);
+                const uint32_t* r32 = reinterpret_cast<const uint32_t*>(tile) + (b0 >> 2);
                 const uint32_t sh = 8 * (b0 & 3);
+                const uint64_t mult = 1ull << bits;
                 uint32_t r[7], a[6];
 #pragma unroll
                 for (int i = 0; i < 7; i++) r[i] = r32[i];
 #pragma unroll
                 for (int i = 0; i < 6; i++) a[i] = __funnelshift_r(r[i], r[i + 1], sh);
 #pragma unroll
-                for (uint32_t j = 0; j < 24; j++) {
-                    if (j < K) {
-                        uint64_t c = base + j < n ? lut[(a[j >> 2] >> (8 * (j & 3))) & 0xFFu] : 0;
-                        x |= c << (64 - bits * (j + 1));
-                    }
-                }
+                for (uint32_t j = 0; j < 24; j++)
+                    if (j < K) x = x * mult + lut[(a[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+                x <<= 64 - K * bits;
             } else {
                 for (uint32_t j = 0; j < K; j++) {
-                    uint64_t c = base + j < n ? lut[raw[threadIdx.x * K + j]] : 0;
+                    uint64_t c = base + j < n ? lut[tile[threadIdx.x * K + j]] : 0;
                     x |= c << (64 - bits * (j + 1));
                 }
             }
             words[w] = x;
         }
+        if (cls2) {
+            // this tile's packed2 words; the last tile also writes the padding words behind the text
+            const uint64_t first2 = byte0 / 32;
+            const uint64_t end2 = b + 1 == blocks ? num_words2 : first2 + tile_bytes / 32;
+            for (uint64_t w2 = first2 + threadIdx.x; w2 < end2; w2 += kBlock) {
+                const uint32_t t = (uint32_t)(w2 - first2);
+                uint32_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (t * 32 < tile_bytes) {
+                    const uint4 lo4 = reinterpret_cast<const uint4*>(tile)[2 * t];
+                    const uint4 hi4 = reinterpret_cast<const uint4*>(tile)[2 * t + 1];
+                    bytes[0] = lo4.x; bytes[1] = lo4.y; bytes[2] = lo4.z; bytes[3] = lo4.w;
+                    bytes[4] = hi4.x; bytes[5] = hi4.y; bytes[6] = hi4.z; bytes[7] = hi4.w;
+                }
+                const uint64_t base2 = w2 * 32;
+                uint32_t xh = 0, xl = 0, m = 0;  // symbols 0..15 / 16..31 of the word, irregular bits
+                if (base2 + 32 <= n) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 16; j++) {
+                        const uint32_t c = lut2[(bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+                        xh = xh * 4 + (c & 3u);
+                        m = m * 2 + (c >> 2);
+                    }
+#pragma unroll
+                    for (uint32_t j = 16; j < 32; j++) {
+                        const uint32_t c = lut2[(bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+                        xl = xl * 4 + (c & 3u);
+                        m = m * 2 + (c >> 2);
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) {
+                        const uint32_t byte = (bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                        const uint32_t c = base2 + j < n ? lut2[byte] : 4u;  // beyond the text: irregular, class 0
+                        if (j < 16) xh = xh * 4 + (c & 3u); else xl = xl * 4 + (c & 3u);
+                        m = m * 2 + (c >> 2);
+                    }
+                }
+                packed2[w2] = ((uint64_t)xh << 32) | xl;
+                // irr is addressed as 64-bit words with symbol 0 in the top bit: 32-bit halves are swapped on little-endian
+                irr32[w2 ^ 1] = m;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -418,6 +446,8 @@ __global__ void __launch_bounds__(kBlock) select_fast2_kernel(KeySpec ks, uint64
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t chunk = (uint64_t)WARPS * 1024;
     const uint64_t chunks = (n + chunk - 1) / chunk;
+    const uint32_t bin0 = (uint32_t)(lo >> (64 - kShardHistBits));
+    const uint32_t span = (hi == 0 ? 1u << kShardHistBits : (uint32_t)(hi >> (64 - kShardHistBits))) - bin0;
     for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
         const uint64_t W0 = c * chunk + (uint64_t)warp * 1024;
         const uint64_t q = (W0 >> 5) + lane;
@@ -430,15 +460,28 @@ __global__ void __launch_bounds__(kBlock) select_fast2_kernel(KeySpec ks, uint64
         const uint64_t i1 = __shfl_sync(0xffffffffu, ir, (lane >> 1) + 1);
         const uint64_t M = (lane & 1) ? ((i0 << 32) | (i1 >> 32)) : i0;  // irregular bits of positions P0 .. P0+63
         const uint64_t P0 = W0 + 32u * lane;
+        // Fast test (no irregular symbol among the 32 that follow, which also means "inside the text"): the
+        // shard is a range of 12-bit histogram bins, so the top 32 key bits decide.  Everything else -- and every
+        // position when a regular byte can be filtered out -- takes the exact path.
+        const uint32_t w_hi = (uint32_t)(w >> 32), w_lo = (uint32_t)w, wn_hi = (uint32_t)(wn >> 32);
+        uint32_t m_hi = (uint32_t)(M >> 32), m_lo = (uint32_t)M;
+        if (filter && !ks.reg_indexed) m_hi = m_lo = ~0u;
         uint32_t T = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-            uint64_t key = (j ? ((w << (2 * j)) | (wn >> ((64 - 2 * j) & 63))) : w) & ~3ull;
-            const uint64_t m = (M << j) & kWin;
-            const uint64_t p = P0 + j;
-            if (m) key = p < n ? first_key_fast2_slow(ks, p) : 0ull;
-            bool take = p < n && key >= lo && (hi == 0 || key < hi);
-            if (take && filter && (!ks.reg_indexed || (m >> 63))) take = indexed_byte(ks.text[p]);
+            const uint32_t khi = j < 16 ? __funnelshift_l(w_lo, w_hi, 2 * j) : __funnelshift_l(wn_hi, w_lo, 2 * j - 32);
+            const uint32_t mj = __funnelshift_l(m_lo, m_hi, j);
+            bool take;
+            if (mj == 0) {
+                take = ((khi >> (32 - kShardHistBits)) - bin0) < span;
+            } else {
+                const uint64_t p = P0 + j;
+                take = false;
+                if (p < n && (!filter || indexed_byte(ks.text[p]))) {
+                    const uint64_t key = first_key_fast2_slow(ks, p);
+                    take = key >= lo && (hi == 0 || key < hi);
+                }
+            }
             T |= (take ? 1u : 0u) << j;
         }
         // dense enumeration of the taken positions

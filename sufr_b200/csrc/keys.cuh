@@ -49,6 +49,7 @@ struct KeySpec {
 // bits 63..2 = 31 symbols.  The radix sort covers only the top kFast2SortBits (4 passes); groups of up to
 // kFast2SmallGroup keys that tie on those bits are then ordered by their full keys in registers
 // (fast2_group_sort_kernel), larger groups and exact ties on all 31 symbols go to the 3-bit refinement.
+constexpr int kShardHistBits = 12;   // multi-GPU key ranges are cut at multiples of 2^(64 - kShardHistBits)
 constexpr int kFast2Symbols = 31;
 constexpr int kFast2SortBits = 32;
 constexpr int kFast2ProbeBits = 40;  // the repetitiveness probe sorts its sample deeper
