@@ -92,21 +92,25 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t* counts, uin
     }
 }
 
+#ifndef SUFR_RSORT_MIN_CTAS
+#define SUFR_RSORT_MIN_CTAS 2
+#endif
 template <typename K, typename V, int IPT>
-__global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+__global__ void __launch_bounds__(BLOCK, SUFR_RSORT_MIN_CTAS) downsweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
                                                           const V* __restrict__ vin, V* __restrict__ vout,
                                                           uint64_t n, int shift, uint32_t dmask,
                                                           const uint32_t* __restrict__ bases,
                                                           uint32_t tiles_per_block) {
     constexpr int TILE = BLOCK * IPT;
-    constexpr size_t EX_BYTES = (sizeof(K) > sizeof(V) ? sizeof(K) : sizeof(V)) * TILE;
     __shared__ uint32_t wc[WARPS][RADIX];   // per-warp digit counters -> tile-local start of (warp, digit)
     __shared__ uint32_t running[RADIX];     // global write cursor of each digit for this block
     __shared__ uint32_t goff[RADIX];        // global index = goff[d] + tile-local slot (mod 2^32)
     __shared__ uint32_t warp_tot[WARPS];
-    __shared__ __align__(16) unsigned char ex_raw[EX_BYTES];
+    // keys and values in tile-local sorted order: separate buffers (dynamic shared memory, > 48 KB together), so
+    // the registers are free as soon as both are exchanged
+    extern __shared__ __align__(16) unsigned char ex_raw[];
     K* exk = reinterpret_cast<K*>(ex_raw);
-    V* exv = reinterpret_cast<V*>(ex_raw);
+    V* exv = reinterpret_cast<V*>(ex_raw + sizeof(K) * TILE);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
 
         K key[IPT];
         V val[IPT];
-        uint32_t slot[IPT];
+        uint16_t slot[IPT];
 #pragma unroll
         for (int i = 0; i < IPT; i++) {
             uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
@@ -139,35 +143,42 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
         for (int i = 0; i < WARPS; i++) wc[i][tid] = 0;
         __syncthreads();
 
-        // warp-level ranking: items are visited in tile order (warp, i, lane) => stable
+        // warp-level ranking: items are visited in tile order (warp, i, lane) => stable.
+        // Pass 1: lanes holding the same digit, by one vote per digit bit (match.any saturates the ADU pipe:
+        // profiles/r1_v0_downsweep_match_any_raw.csv).  All rows' votes are independent of each other.
+        uint32_t peers_of[IPT];
 #pragma unroll
         for (int i = 0; i < IPT; i++) {
-            uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
-            bool valid = idx < count;
             uint32_t d = digit_of(key[i], shift, dmask);
             // valid lanes of this row, computed instead of voted (votes are the bottleneck of this kernel)
             int rem = (int)count - (int)(warp * (32 * IPT) + i * 32);
             unsigned vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-            uint32_t r = 0;
-            if (valid) {
-                // lanes holding the same digit, by one vote per digit bit (match.any saturates the ADU pipe:
-                // profiles/r1_v0_downsweep_match_any_raw.csv)
-                unsigned peers = vm;
+            unsigned peers = vm;
+            if (vm) {  // warp-uniform
 #pragma unroll
                 for (int b = 0; b < RADIX_BITS; b++) {
-                    unsigned vote = __ballot_sync(vm, (d >> b) & 1u);
+                    unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
                     peers &= ((d >> b) & 1u) ? vote : ~vote;
                 }
-                int leader = __ffs(peers) - 1;
-                uint32_t old = 0;
-                if (lane == leader) {
-                    old = wc[warp][d];
-                    wc[warp][d] = old + __popc(peers);
-                }
-                old = __shfl_sync(peers, old, leader);
-                r = old + __popc(peers & lt_mask);
             }
-            slot[i] = r;
+            peers_of[i] = ((vm >> lane) & 1u) ? peers : 0u;
+        }
+        // Pass 2: the serial chain through the per-warp digit counters.  The shuffle uses the FULL mask (every lane
+        // is here; lanes without an element read lane 31 and ignore it): a shuffle under the per-group mask
+        // `peers` is executed once per distinct digit of the row and was half of the ranking cost
+        // (tools/ubench/warp_prims.cu: 65 -> 32 SM-cycles per row).
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const unsigned peers = peers_of[i];
+            const uint32_t d = digit_of(key[i], shift, dmask);
+            const int leader = __ffs(peers) - 1;  // -1 for lanes without an element
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = wc[warp][d];
+                wc[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader & 31);
+            slot[i] = (uint16_t)(old + __popc(peers & lt_mask));
             __syncwarp();
         }
         __syncthreads();
@@ -199,38 +210,26 @@ __global__ void __launch_bounds__(BLOCK) downsweep_kernel(const K* __restrict__ 
         for (int w = 0; w < WARPS; w++) wc[w][tid] += tile_start;
         __syncthreads();
 
-        // exchange keys through shared memory so that the global writes are digit-contiguous
+        // exchange through shared memory so that the global writes are digit-contiguous
 #pragma unroll
         for (int i = 0; i < IPT; i++) {
             uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
             if (idx < count) {
-                uint32_t d = digit_of(key[i], shift, dmask);
-                slot[i] += wc[warp][d];
-                exk[slot[i]] = key[i];
+                uint32_t s = slot[i] + wc[warp][digit_of(key[i], shift, dmask)];
+                exk[s] = key[i];
+                exv[s] = val[i];
             }
         }
         __syncthreads();
-        uint32_t dst[IPT];
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
             uint32_t s = k * BLOCK + tid;
             if (s < count) {
                 K kk = exk[s];
-                dst[k] = goff[digit_of(kk, shift, dmask)] + s;
-                kout[dst[k]] = kk;
+                uint32_t dst = goff[digit_of(kk, shift, dmask)] + s;
+                kout[dst] = kk;
+                vout[dst] = exv[s];
             }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < IPT; i++) {
-            uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
-            if (idx < count) exv[slot[i]] = val[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < IPT; k++) {
-            uint32_t s = k * BLOCK + tid;
-            if (s < count) vout[dst[k]] = exv[s];
         }
         __syncthreads();
     }
@@ -245,7 +244,7 @@ template <typename K, typename V>
 inline Plan make_plan(uint64_t n) {
     constexpr int TILE = BLOCK * Tuning<K, V>::IPT;
     uint64_t tiles = div_up(n, TILE);
-    uint64_t max_grid = (uint64_t)kNumSMs * 4;  // 4 resident CTAs per SM worth of chunks
+    uint64_t max_grid = (uint64_t)kNumSMs * 4;  // two full waves of the 2 resident CTAs per SM
     Plan p;
     p.grid = (uint32_t)(tiles < max_grid ? (tiles ? tiles : 1) : max_grid);
     p.tiles_per_block = (uint32_t)div_up(tiles ? tiles : 1, p.grid);
@@ -267,6 +266,13 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
     constexpr int IPT = Tuning<K, V>::IPT;
     if (n == 0 || end_bit <= begin_bit) return false;
     Plan p = make_plan<K, V>(n);
+    constexpr size_t ex_bytes = (sizeof(K) + sizeof(V)) * BLOCK * IPT;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        SUFR_CUDA_CHECK(cudaFuncSetAttribute(downsweep_kernel<K, V, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ex_bytes));
+        attr_set = true;
+    }
     bool in_b = false;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
         int nb = end_bit - bit < RADIX_BITS ? end_bit - bit : RADIX_BITS;
@@ -285,7 +291,7 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
             SUFR_CUDA_CHECK(cudaEventCreate(&e1));
             SUFR_CUDA_CHECK(cudaEventRecord(e0, stream));
         }
-        downsweep_kernel<K, V, IPT><<<p.grid, BLOCK, 0, stream>>>(kin, kout, vin, vout, n, bit, dmask, counts,
+        downsweep_kernel<K, V, IPT><<<p.grid, BLOCK, ex_bytes, stream>>>(kin, kout, vin, vout, n, bit, dmask, counts,
                                                                  p.tiles_per_block);
         SUFR_KERNEL_CHECK();
         if (downsweep_events) {
