@@ -15,6 +15,8 @@
 
 #include "common.cuh"
 
+#include <cuda_pipeline.h>
+
 namespace sufr {
 namespace rsort {
 
@@ -106,11 +108,14 @@ __global__ void __launch_bounds__(BLOCK, SUFR_RSORT_MIN_CTAS) downsweep_kernel(c
     __shared__ uint32_t running[RADIX];     // global write cursor of each digit for this block
     __shared__ uint32_t goff[RADIX];        // global index = goff[d] + tile-local slot (mod 2^32)
     __shared__ uint32_t warp_tot[WARPS];
-    // keys and values in tile-local sorted order: separate buffers (dynamic shared memory, > 48 KB together), so
-    // the registers are free as soon as both are exchanged
+    // Dynamic shared memory (> 48 KB): exk / exv hold the tile in tile-local sorted order (separate buffers, so the
+    // registers are free as soon as both are exchanged); pk / pv receive the NEXT tile by cp.async while this one
+    // is ranked, exchanged and scattered, so no warp waits on global loads at the top of the loop.
     extern __shared__ __align__(16) unsigned char ex_raw[];
     K* exk = reinterpret_cast<K*>(ex_raw);
     V* exv = reinterpret_cast<V*>(ex_raw + sizeof(K) * TILE);
+    K* pk = reinterpret_cast<K*>(ex_raw + (sizeof(K) + sizeof(V)) * TILE);
+    V* pv = reinterpret_cast<V*>(ex_raw + (2 * sizeof(K) + sizeof(V)) * TILE);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -121,6 +126,27 @@ __global__ void __launch_bounds__(BLOCK, SUFR_RSORT_MIN_CTAS) downsweep_kernel(c
     uint64_t t1 = t0 + tiles_per_block;
     if (t1 > total_tiles) t1 = total_tiles;
 
+    // 16-byte chunks; elements beyond the end of the input are zero-filled
+    auto prefetch = [&](uint64_t t) {
+        const uint64_t base = t * TILE;
+        const uint32_t cnt = (n - base) < (uint64_t)TILE ? (uint32_t)(n - base) : (uint32_t)TILE;
+        constexpr uint32_t KPC = 16 / sizeof(K), VPC = 16 / sizeof(V);  // elements per chunk
+        for (uint32_t c = tid; c < TILE / KPC; c += BLOCK) {
+            const uint32_t e = c * KPC;
+            const uint32_t valid = cnt > e ? (cnt - e < KPC ? cnt - e : KPC) : 0u;
+            __pipeline_memcpy_async(pk + e, valid ? kin + base + e : kin, 16, 16 - valid * sizeof(K));
+        }
+        for (uint32_t c = tid; c < TILE / VPC; c += BLOCK) {
+            const uint32_t e = c * VPC;
+            const uint32_t valid = cnt > e ? (cnt - e < VPC ? cnt - e : VPC) : 0u;
+            __pipeline_memcpy_async(pv + e, valid ? vin + base + e : vin, 16, 16 - valid * sizeof(V));
+        }
+        __pipeline_commit();
+    };
+    if (t0 < t1) prefetch(t0);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+
     for (uint64_t t = t0; t < t1; t++) {
         const uint64_t base = t * TILE;
         const uint32_t count = (n - base) < (uint64_t)TILE ? (uint32_t)(n - base) : (uint32_t)TILE;
@@ -130,18 +156,14 @@ __global__ void __launch_bounds__(BLOCK, SUFR_RSORT_MIN_CTAS) downsweep_kernel(c
         uint16_t slot[IPT];
 #pragma unroll
         for (int i = 0; i < IPT; i++) {
-            uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
-            if (idx < count) {
-                key[i] = kin[base + idx];
-                val[i] = vin[base + idx];
-            } else {
-                key[i] = 0;
-                val[i] = 0;
-            }
+            const uint32_t idx = warp * (32 * IPT) + i * 32 + lane;
+            key[i] = pk[idx];
+            val[i] = pv[idx];
         }
 #pragma unroll
         for (int i = 0; i < WARPS; i++) wc[i][tid] = 0;
         __syncthreads();
+        if (t + 1 < t1) prefetch(t + 1);  // every thread has read its part of pk / pv
 
         // warp-level ranking: items are visited in tile order (warp, i, lane) => stable.
         // Pass 1: lanes holding the same digit, by one vote per digit bit (match.any saturates the ADU pipe:
@@ -231,6 +253,7 @@ __global__ void __launch_bounds__(BLOCK, SUFR_RSORT_MIN_CTAS) downsweep_kernel(c
                 vout[dst] = exv[s];
             }
         }
+        __pipeline_wait_prior(0);
         __syncthreads();
     }
 }
@@ -266,7 +289,7 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
     constexpr int IPT = Tuning<K, V>::IPT;
     if (n == 0 || end_bit <= begin_bit) return false;
     Plan p = make_plan<K, V>(n);
-    constexpr size_t ex_bytes = (sizeof(K) + sizeof(V)) * BLOCK * IPT;
+    constexpr size_t ex_bytes = 2 * (sizeof(K) + sizeof(V)) * BLOCK * IPT;  // exchange + prefetch buffers
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         SUFR_CUDA_CHECK(cudaFuncSetAttribute(downsweep_kernel<K, V, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
