@@ -226,6 +226,8 @@ class Build {
     DevBuf<uint64_t> d_nstarts, d_nends;
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
+    DevBuf<uint64_t> keys_spare_;  // fast path: the radix sort's ping-pong partners, output of the fused round 0
+    DevBuf<uint32_t> pos_spare_;
     DevBuf<uint32_t> d_isa;     // inverse suffix array (only when prefix doubling ran)
     DevBuf<uint32_t> d_counts;  // radix sort count matrix
     uint64_t shard_offset = 0, shard_count = 0, total_suffixes = 0;
@@ -596,11 +598,13 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     if (in_b) {
         keys_sorted = std::move(keys_b);
         d_sa = std::move(pos_b);
+        if (ks.fast2) { keys_spare_ = std::move(keys_a); pos_spare_ = std::move(pos_a); }
     } else {
         keys_sorted = std::move(keys_a);
         d_sa = std::move(pos_a);
+        if (ks.fast2) { keys_spare_ = std::move(keys_b); pos_spare_ = std::move(pos_b); }
     }
-    // the ping-pong partners are released here (end of scope)
+    // the ping-pong partners are released here (end of scope), except on the fast path (see refine)
 }
 
 // Stable sort of (ck, pos) on the low `key_bits` bits of the composite key.
@@ -631,14 +635,22 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     int word = fast2 ? -1 : 0;
     int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
     DevBuf<uint32_t> large;  // fast path: members of large groups that the register sort left alone
+    const bool fused0 = fast2 && !getenv("SUFR_B200_DEBUG_UNFUSED_ROUND0");
     if (fast2) {
         large = dalloc<uint32_t>(r0n / 32 + 1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(large.get(), 0, (r0n / 32 + 1) * 4, st()));
-        fast2_group_sort_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get());
-        SUFR_KERNEL_CHECK();
-        launched();
+        if (!fused0) {
+            fast2_group_sort_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+        }
     }
-    ViewAll v0{keys_sorted.get(), d_sa.get(), fast2 ? large.get() : nullptr};
+    if (!fused0) {
+        keys_spare_.reset();
+        pos_spare_.reset();
+    }
+    ViewAll v0{fused0 ? keys_spare_.get() : keys_sorted.get(), fused0 ? pos_spare_.get() : d_sa.get(),
+               fast2 ? large.get() : nullptr};
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, pos, seg;
     {
@@ -648,7 +660,11 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         auto act_pos = dalloc<uint32_t>(capacity);
         auto d_cnt = dalloc<unsigned long long>(1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
-        if (fast2) {
+        if (fused0) {
+            round0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), keys_spare_.get(),
+                                                                      pos_spare_.get(), r0n, large.get(), d_lcp.get(),
+                                                                      act_slot.get(), act_pos.get(), d_cnt.get(), capacity);
+        } else if (fast2) {
             resolve0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get(),
                                                                         d_lcp.get(), act_slot.get(), act_pos.get(),
                                                                         d_cnt.get(), capacity);
@@ -659,6 +675,10 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         }
         SUFR_KERNEL_CHECK();
         launched();
+        if (fused0) {  // the ordered records are in the partners now
+            keys_sorted = std::move(keys_spare_);
+            d_sa = std::move(pos_spare_);
+        }
         if (final_word) {
             keys_sorted.reset();
             return;

@@ -894,6 +894,194 @@ __global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* 
     }
 }
 
+// Group ordering and round 0 of the fast path in ONE pass over the radix-sorted records (the two kernels above,
+// fused; same results).  Per tile of 1024 records (+ 9 before, + 8 behind) staged in shared memory:
+//   phase 0: bitmap of run heads (record whose sorted bits differ from its predecessor's); from it every record
+//            gets the extent of its run with two shifts and a clz / ffs.  A run of >= 9 records is "large";
+//   phase 1: records of runs of 2..8 compute their rank inside the run by counting (every thread does the same
+//            bounded work, no per-group serial sorting) -> the tile in final order in a second buffer;
+//   phase 2: per record this tile owns (its run's head lies in the tile, or the run is large and the record itself
+//            does): boundary LCP / pending / fix-up and the unresolved flag exactly as resolve0_fast2_kernel;
+//            unresolved records are appended with one global atomic per tile.
+// Runs that are cut off by the staging window are either long enough to be known large or are not adjacent to
+// anything this tile emits.  OUT OF PLACE (the radix sort's ping-pong partners receive the ordered records): a tile
+// reads records that a neighbouring tile orders, so an in-place update would race.
+constexpr int kR0Tile = 1024, kR0Back = kFast2SmallGroup + 1, kR0Fwd = kFast2SmallGroup;
+constexpr int kR0N = kR0Tile + kR0Back + kR0Fwd;
+constexpr int kR0Steps = (kR0N + 1 + kBlock - 1) / kBlock;
+struct RunExtent {
+    uint32_t back, fwd;  // records of the same run before / behind (32 = "32 or more")
+    uint32_t pback;      // the same `back` for record a-1 (31 = "31 or more")
+};
+__device__ __forceinline__ RunExtent run_extent(const uint32_t* hbm, uint32_t a) {  // hbm[-1] and hbm[+1] exist
+    const uint32_t wi = a >> 5, pos = a & 31;
+    const uint32_t w0 = hbm[(int)wi - 1], w1 = hbm[wi], w2 = hbm[wi + 1];
+    const uint32_t L = __funnelshift_l(w0, w1, 31 - pos);                           // bit 31 = head(a), 30 = head(a-1) ..
+    const uint32_t R = (uint32_t)((((uint64_t)w2 << 32) | w1) >> (pos + 1));        // bit 0 = head(a+1) ..
+    RunExtent e;
+    e.back = L ? (uint32_t)__clz((int)L) : 32u;
+    e.fwd = R ? (uint32_t)__ffs((int)R) - 1u : 32u;
+    e.pback = (L << 1) ? (uint32_t)__clz((int)(L << 1)) : 31u;
+    return e;
+}
+__global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ pos,
+                                                              uint64_t* __restrict__ keys_out,
+                                                              uint32_t* __restrict__ pos_out,
+                                                              uint64_t s, uint32_t* __restrict__ large,
+                                                              uint32_t* __restrict__ lcp,
+                                                              uint32_t* __restrict__ act_slot,
+                                                              uint32_t* __restrict__ act_pos,
+                                                              unsigned long long* __restrict__ act_count,
+                                                              uint64_t capacity) {
+    constexpr uint32_t RL = kFast2SmallGroup + 1;  // a run of RL records or more is "large"
+    __shared__ uint64_t ka[kR0N], kb[kR0N];
+    __shared__ uint32_t pa[kR0N], pb[kR0N];
+    __shared__ uint32_t hbm_raw[kR0Steps * (kBlock / 32) + 2];
+    __shared__ uint32_t wcount[kBlock / 32];
+    __shared__ unsigned long long gbase;
+    uint32_t* hbm = hbm_raw + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        hbm_raw[0] = 0;
+        hbm_raw[kR0Steps * (kBlock / 32) + 1] = 0;
+    }
+    const uint64_t tiles = (s + kR0Tile - 1) / kR0Tile;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * kR0Tile;
+        const uint32_t off = t0 ? (uint32_t)kR0Back : 0u;  // local index of record t0
+        const uint64_t g0 = t0 - off;                       // global index of local record 0
+        const uint32_t cnt = (uint32_t)((s - g0) < (uint64_t)(off + kR0Tile + kR0Fwd) ? (s - g0)
+                                                                                       : (uint64_t)(off + kR0Tile + kR0Fwd));
+        const uint32_t own_end = off + (uint32_t)((s - t0) < (uint64_t)kR0Tile ? (s - t0) : (uint64_t)kR0Tile);
+        __syncthreads();
+        for (uint32_t a = threadIdx.x; a < cnt; a += kBlock) {
+            ka[a] = keys[g0 + a];
+            pa[a] = pos[g0 + a];
+        }
+        __syncthreads();
+        // phase 0: run heads; local record 0 and the end of the staged window count as heads
+#pragma unroll
+        for (int k = 0; k < kR0Steps; k++) {
+            const uint32_t a = threadIdx.x + (uint32_t)k * kBlock;
+            bool hd = a == cnt;
+            if (a < cnt) hd = a == 0 || ((ka[a] ^ ka[a - 1]) & kFast2TopMask) != 0;
+            const uint32_t w = __ballot_sync(0xffffffffu, hd);
+            if (lane == 0) hbm[a >> 5] = w;
+        }
+        __syncthreads();
+        // phase 1: final order of the tile.  A thread owns the same local indices in phases 1 and 2 and runs keep
+        // their index ranges, so the extents are computed once.
+        uint32_t ext[kR0Steps];
+#pragma unroll
+        for (int k = 0; k < kR0Steps; k++) {
+            const uint32_t a = threadIdx.x + (uint32_t)k * kBlock;
+            ext[k] = 0;
+            if (a >= cnt) continue;
+            const RunExtent e = run_extent(hbm, a);
+            ext[k] = e.back | (e.fwd << 8) | (e.pback << 16);
+            const uint64_t key = ka[a];
+            uint32_t na = a;
+            if (e.back + e.fwd + 1 < RL && e.back + e.fwd > 0) {
+                const uint32_t h = a - e.back;
+                uint32_t rank = 0;
+                for (uint32_t b = h; b <= a + e.fwd; b++) {
+                    const uint64_t o = ka[b];
+                    rank += (o < key || (o == key && b < a)) ? 1u : 0u;
+                }
+                na = h + rank;
+            }
+            kb[na] = key;
+            pb[na] = pa[a];
+        }
+        __syncthreads();
+        // phase 2: LCP / flags of the records this tile owns
+        uint32_t act = 0;
+        uint32_t apos[kR0Steps];
+        uint64_t* const keys_t = keys_out + g0;
+        uint32_t* const pos_t = pos_out + g0;
+        uint32_t* const lcp_t = lcp + g0;
+#pragma unroll
+        for (int k = 0; k < kR0Steps; k++) {
+            const uint32_t d = threadIdx.x + (uint32_t)k * kBlock;
+            apos[k] = 0;
+            if (d >= cnt) continue;
+            const uint32_t back = ext[k] & 0xFFu, fwd = (ext[k] >> 8) & 0xFFu, pback = ext[k] >> 16;
+            const bool is_large = back + fwd + 1 >= RL;
+            const uint32_t h = d - back;
+            const bool emit = is_large ? (d >= off && d < own_end) : (h >= off && h < own_end);
+            if (!emit) continue;
+            const bool first = g0 == 0 && d == 0;  // global record 0
+            const uint64_t k0 = kb[d];
+            bool head, next_same;
+            uint32_t out;
+            if (is_large) {  // canonical key = the sorted bits: the whole run is one group
+                head = back == 0;
+                next_same = fwd > 0;
+                out = first ? 0u : (head ? kLcpFixup : kLcpPending);
+            } else {
+                const uint64_t c0 = k0 & ~3ull;
+                next_same = fwd > 0 && (kb[d + 1] & ~3ull) == c0;
+                head = true;
+                out = 0;
+                if (!first) {
+                    const uint64_t km1 = kb[d - 1];
+                    bool prev_multi;
+                    if (back > 0) {  // predecessor in the same (small) run
+                        head = (km1 & ~3ull) != c0;
+                        prev_multi = back >= 2 && ((kb[d - 2] ^ km1) & ~3ull) == 0;
+                    } else {         // predecessor = last record of the previous run
+                        prev_multi = pback > 0 && d >= 2 && (pback + 1 >= RL || ((kb[d - 2] ^ km1) & ~3ull) == 0);
+                    }
+                    if (!head)
+                        out = kLcpPending;
+                    else if (((km1 | k0) & 1ull) == 0 && !next_same && !prev_multi)
+                        out = (uint32_t)__clzll((long long)(km1 ^ k0)) >> 1;
+                    else
+                        out = kLcpFixup;
+                }
+            }
+            lcp_t[d] = out;
+            apos[k] = pb[d];
+            keys_t[d] = k0;
+            pos_t[d] = apos[k];
+            if (is_large) atomicOr(&large[(g0 + d) >> 5], 1u << ((g0 + d) & 31));
+            if (!head || next_same) act |= 1u << k;
+        }
+        // append: per-thread count -> warp prefix -> block prefix -> one atomic
+        const uint32_t mine = __popc(act);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wcount[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int w = 0; w < kBlock / 32; w++) {
+                uint32_t tt = wcount[w];
+                wcount[w] = acc;
+                acc += tt;
+            }
+            gbase = acc ? atomicAdd(act_count, (unsigned long long)acc) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long idx = gbase + wcount[warp] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < kR0Steps; k++) {
+            if (act & (1u << k)) {
+                if (idx < capacity) {
+                    act_slot[idx] = (uint32_t)(g0 + threadIdx.x + (uint32_t)k * kBlock);
+                    act_pos[idx] = apos[k];
+                }
+                idx++;
+            }
+        }
+    }
+}
+
 // Exact LCP of the boundaries the fast path could not read off the keys, from the FINAL suffix order.
 __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
                                                            uint32_t* __restrict__ lcp) {
