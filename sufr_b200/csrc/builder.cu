@@ -521,6 +521,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     DevBuf<uint64_t> keys_a, keys_b;
     DevBuf<uint32_t> pos_a, pos_b;
     const int used_bits = (int)(ks.pt.K * ks.pt.bits);
+    bool first_counts_ready = false;
     uint64_t kept = n;     // suffixes that survive the filter (all ranks' ranges together)
     uint64_t sort_n = n;   // elements handed to the sort
     if (prefilter && n) kept = indexed_count_;
@@ -573,10 +574,21 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         keys_a = dalloc<uint64_t>(n);
         pos_a = dalloc<uint32_t>(n);
         if (n) {
-            if (ks.fast2 && !descending)
-                keygen_fast2_kernel<<<grid_for(n, 8), kBlock, 0, st()>>>(ks, n, sentinel ? 1 : 0, keys_a.get(),
-                                                                        pos_a.get());
-            else
+            if (ks.fast2 && !descending) {
+                // one block per block of the sort's first pass, which then needs no histogram pass of its own
+                static bool attr_set = false;
+                if (!attr_set) {
+                    SUFR_CUDA_CHECK(cudaFuncSetAttribute(keygen_fast2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         kKeygenSmem));
+                    attr_set = true;
+                }
+                const rsort::Plan plan = rsort::make_plan<uint64_t, uint32_t>(n);
+                const uint64_t chunk = (uint64_t)plan.tiles_per_block * rsort::BLOCK * rsort::Tuning<uint64_t, uint32_t>::IPT;
+                d_counts = dalloc<uint32_t>(rsort::counts_words());
+                keygen_fast2_kernel<<<plan.grid, kBlock, kKeygenSmem, st()>>>(ks, n, sentinel ? 1 : 0, keys_a.get(), pos_a.get(),
+                                                                             chunk, 64 - kFast2SortBits, d_counts.get());
+                first_counts_ready = true;
+            } else
                 keygen_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, descending, d_text.get(), sentinel ? 1 : 0,
                                                                   keys_a.get(), pos_a.get());
             SUFR_KERNEL_CHECK();
@@ -586,13 +598,13 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     t_keys_mark = timer.mark();
     keys_b = dalloc<uint64_t>(sort_n);
     pos_b = dalloc<uint32_t>(sort_n);
-    d_counts = dalloc<uint32_t>(rsort::counts_words());
+    if (!first_counts_ready) d_counts = dalloc<uint32_t>(rsort::counts_words());
     // 3-bit keys: all used bits (sentinel keys have the unused low bits set, so those join the sort then).
     // 2-bit fast path: only the top kFast2SortBits; ties go to the exact refinement.
     const int begin_bit = ks.fast2 ? 64 - kFast2SortBits : (sentinel ? 0 : 64 - used_bits);
     bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), sort_n,
                                                       begin_bit, 64, d_counts.get(), st(), &ctx.launches,
-                                                      &downsweep_events);
+                                                      &downsweep_events, first_counts_ready);
     sorted_elements = sort_n;
     sort_n_ = sort_n;
     if (in_b) {
@@ -1105,10 +1117,9 @@ void Build::run(SufrB200Result* out) {
         sa64 = dalloc<unsigned long long>(s);
         lcp64 = dalloc<unsigned long long>(s);
         if (s) {
-            widen_kernel<<<grid_for(s, 2), kBlock, 0, st()>>>(s, d_sa.get(), sa64.get());
-            widen_kernel<<<grid_for(s, 2), kBlock, 0, st()>>>(s, d_lcp.get(), lcp64.get());
+            widen2_kernel<<<grid_for(s, 8), kBlock, 0, st()>>>(s, d_sa.get(), d_lcp.get(), sa64.get(), lcp64.get());
             SUFR_KERNEL_CHECK();
-            launched(2);
+            launched();
         }
         d_sa.reset();
         d_lcp.reset();

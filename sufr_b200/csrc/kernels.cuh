@@ -255,25 +255,73 @@ __global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, 
     }
 }
 
-// Fast-path variant of keygen_kernel: warp-window key generation (keys.cuh::Fast2Window), ascending order.
+// Fast-path variant of keygen_kernel, ascending order.  A warp owns 1024 consecutive positions and lane l the 32
+// positions of packed2 word l, so a key is two funnel shifts of registers the lane already holds; the 32 x 32 keys
+// are transposed through shared memory (in two halves of 16 keys per lane, which keeps four blocks of the sort's
+// 4-per-SM grid resident) so that the stores are coalesced.  Block b generates exactly the records
+// of block b of the radix sort's first pass (`chunk_elems` = tiles_per_block x tile) and leaves that pass's digit
+// histogram in `counts` ([digit][block], what rsort::upsweep_kernel would compute from the keys).
+constexpr int kKeygenSmem = (kBlock / 32) * 32 * 17 * 8;
 __global__ void __launch_bounds__(kBlock) keygen_fast2_kernel(KeySpec ks, uint64_t n, int filter,
-                                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t chunks = (n + 1023) >> 10;
-    for (uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < chunks; c += warps) {
-        const uint64_t W0 = c << 10;
-        Fast2Window fw = fast2_window_load(ks, W0, lane);
-#pragma unroll 4
-        for (int r = 0; r < 32; r++) {
-            uint64_t k = fast2_window_key(ks, fw, W0, r, lane);
-            uint64_t p = W0 + (uint64_t)r * 32 + lane;
-            if (p < n) {
-                keys[p] = (filter && !indexed_byte(ks.text[p])) ? ~0ull : k;
-                pos[p] = (uint32_t)p;
+                                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ pos,
+                                                              uint64_t chunk_elems, int hist_shift,
+                                                              uint32_t* __restrict__ counts) {
+    constexpr int WARPS = kBlock / 32;
+    extern __shared__ __align__(16) uint64_t keygen_tr[];  // [WARPS][32][17]
+    __shared__ uint32_t hist[WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < WARPS * 256; i += kBlock) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    uint64_t* T = keygen_tr + (size_t)warp * 32 * 17;
+    const uint64_t begin = (uint64_t)blockIdx.x * chunk_elems;
+    const uint64_t end = begin + chunk_elems < n ? begin + chunk_elems : n;
+    for (uint64_t W0 = begin + (uint64_t)warp * 1024; W0 < end; W0 += (uint64_t)WARPS * 1024) {
+        const uint64_t q = (W0 >> 5) + lane;
+        const uint64_t w = q < ks.packed2_words ? __ldg(ks.packed2 + q) : 0ull;
+        uint64_t wn = __shfl_down_sync(0xffffffffu, w, 1);
+        if (lane == 31) wn = q + 1 < ks.packed2_words ? __ldg(ks.packed2 + q + 1) : 0ull;
+        const uint64_t qi = (W0 >> 6) + lane;
+        const uint64_t ir = (lane <= 16 && qi < ks.irr_words) ? __ldg(ks.irr + qi) : ~0ull;
+        const uint64_t i0 = __shfl_sync(0xffffffffu, ir, lane >> 1);
+        const uint64_t i1 = __shfl_sync(0xffffffffu, ir, (lane >> 1) + 1);
+        uint64_t M = (lane & 1) ? ((i0 << 32) | (i1 >> 32)) : i0;  // irregular bits of positions P0 .. P0+63
+        if (filter && !ks.reg_indexed) M = ~0ull;                 // a regular byte may be filtered: exact path everywhere
+        const uint64_t P0 = W0 + 32u * lane;
+        constexpr uint64_t kWin = ~0ull << (64 - kFast2Symbols);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int jj = 0; jj < 16; jj++) {
+                const int j = 16 * h + jj;
+                uint64_t key = (j ? ((w << (2 * j)) | (wn >> (64 - 2 * j))) : w) & ~3ull;
+                if ((M << j) & kWin) {  // irregular symbol in the window (rare): exact key, and the suffix filter
+                    const uint64_t p = P0 + j;
+                    key = 0;
+                    if (p < n) key = (filter && !indexed_byte(ks.text[p])) ? ~0ull : first_key_fast2_slow(ks, p);
+                }
+                T[lane * 17 + jj] = key;
             }
+            __syncwarp();
+            // two rows of 16 keys per store instruction
+#pragma unroll 4
+            for (int it = 0; it < 16; it++) {
+                const int r = 2 * it + (lane >> 4), jj = lane & 15;
+                const uint64_t p = W0 + 32u * r + 16u * h + jj;
+                if (p < n) {
+                    const uint64_t key = T[r * 17 + jj];
+                    keys[p] = key;
+                    pos[p] = (uint32_t)p;
+                    atomicAdd(&hist[warp][(uint32_t)(key >> hist_shift) & 255u], 1u);
+                }
+            }
+            __syncwarp();
         }
     }
+    __syncthreads();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < WARPS; w2++) acc += hist[w2][threadIdx.x];
+    counts[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x] = acc;
 }
 
 // Repetitiveness probe: first keys of every `stride`-th position; after sorting them, the number of adjacent
@@ -1706,10 +1754,25 @@ __global__ void __launch_bounds__(kBlock) lcp_to_u8_kernel(const uint32_t* __res
     }
 }
 
-__global__ void __launch_bounds__(kBlock) widen_kernel(uint64_t m, const uint32_t* __restrict__ src,
-                                                       unsigned long long* __restrict__ dst) {
+// Both result arrays in one launch: 16-byte loads, two 16-byte streaming stores per load (arrays 16-byte aligned).
+__global__ void __launch_bounds__(kBlock) widen2_kernel(uint64_t m, const uint32_t* __restrict__ sa,
+                                                        const uint32_t* __restrict__ lcp,
+                                                        unsigned long long* __restrict__ sa64,
+                                                        unsigned long long* __restrict__ lcp64) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) dst[a] = src[a];
+    const uint64_t nvec = m / 4;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(sa) + v);
+        const uint4 b = __ldcs(reinterpret_cast<const uint4*>(lcp) + v);
+        __stcs(reinterpret_cast<ulonglong2*>(sa64) + 2 * v, make_ulonglong2(a.x, a.y));
+        __stcs(reinterpret_cast<ulonglong2*>(sa64) + 2 * v + 1, make_ulonglong2(a.z, a.w));
+        __stcs(reinterpret_cast<ulonglong2*>(lcp64) + 2 * v, make_ulonglong2(b.x, b.y));
+        __stcs(reinterpret_cast<ulonglong2*>(lcp64) + 2 * v + 1, make_ulonglong2(b.z, b.w));
+    }
+    for (uint64_t i = nvec * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        sa64[i] = sa[i];
+        lcp64[i] = lcp[i];
+    }
 }
 
 // ------------------------------------------------------------------ synthetic workloads (bench.py)
