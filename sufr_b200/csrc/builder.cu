@@ -226,6 +226,21 @@ class Build {
     DevBuf<uint64_t> d_nstarts, d_nends;
     std::vector<uint64_t> n_ranges_host;
     DevBuf<uint32_t> d_sa, d_lcp;
+    // 64-bit device results of the fast path: round 0 writes them directly, the (few) entries the refinement
+    // changes afterwards are patched in at the end, so the full-array widening pass disappears.  Dropped (and the
+    // widening pass used) as soon as something rewrites the arrays wholesale: prefix doubling, the post-sort
+    // filter, the N-run rule, shard slicing.
+    DevBuf<unsigned long long> wide_sa_, wide_lcp_;
+    DevBuf<uint32_t> wide_slots_;
+    uint64_t wide_m_ = 0;
+    bool wide_ok_ = false;
+    void drop_wide() {
+        wide_ok_ = false;
+        wide_sa_.reset();
+        wide_lcp_.reset();
+        wide_slots_.reset();
+        wide_m_ = 0;
+    }
     DevBuf<uint64_t> keys_spare_;  // fast path: the radix sort's ping-pong partners, output of the fused round 0
     DevBuf<uint32_t> pos_spare_;
     DevBuf<uint32_t> d_isa;     // inverse suffix array (only when prefix doubling ran)
@@ -673,9 +688,23 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         auto d_cnt = dalloc<unsigned long long>(1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
         if (fused0) {
+            drop_wide();
+            if (index_bits_ == 64 && result_memory_ == SUFR_B200_MEM_DEVICE && !args.allow_ambiguity &&
+                !getenv("SUFR_B200_DEBUG_NO_EARLY_WIDE")) {
+                // only when the two extra arrays fit beside the sort buffers that are still alive
+                size_t free_b = 0, total_b = 0;
+                SUFR_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+                const size_t fits = std::min<size_t>(2, ctx.pool.count_fits(8 * r0n));
+                if (free_b > (2 - fits) * 8 * r0n + (4ull << 30)) {
+                    wide_sa_ = dalloc<unsigned long long>(r0n);
+                    wide_lcp_ = dalloc<unsigned long long>(r0n);
+                    wide_ok_ = true;
+                }
+            }
             round0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), keys_spare_.get(),
                                                                       pos_spare_.get(), r0n, large.get(), d_lcp.get(),
-                                                                      act_slot.get(), act_pos.get(), d_cnt.get(), capacity);
+                                                                      act_slot.get(), act_pos.get(), d_cnt.get(), capacity,
+                                                                      wide_sa_.get(), wide_lcp_.get());
         } else if (fast2) {
             resolve0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get(),
                                                                         d_lcp.get(), act_slot.get(), act_pos.get(),
@@ -712,10 +741,16 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             if (in_b) { std::swap(act_slot, slot_b); std::swap(act_pos, pos_b); }
             slot = std::move(act_slot);
             pos = std::move(act_pos);
+            if (wide_ok_) {  // every later change of SA / LCP happens at one of these slots (or is an LCP fix-up)
+                wide_slots_ = dalloc<uint32_t>(m);
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(wide_slots_.get(), slot.get(), m * 4, cudaMemcpyDeviceToDevice, st()));
+                wide_m_ = m;
+            }
             seg = dalloc<uint32_t>(m);
             nseg = scan_total(m, SparseSegIn{v0, slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
         } else {
             // dense (repetitive text): order-preserving compaction by scan
+            drop_wide();
             act_slot.reset();
             act_pos.reset();
             DevBuf<unsigned long long> part;
@@ -940,7 +975,8 @@ void Build::sort_phase(bool prefilter, bool sharded) {
     t_sorted_mark = timer.mark();
     refine(keys_sorted);
     if (ks.fast2 && s) {
-        lcp_fixup_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get());
+        lcp_fixup_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get(),
+                                                              wide_ok_ ? wide_lcp_.get() : nullptr);
         SUFR_KERNEL_CHECK();
         launched();
     }
@@ -1022,6 +1058,9 @@ void Build::run(SufrB200Result* out) {
         d_sa.reset();
         d_lcp.reset();
         d_isa.reset();
+        drop_wide();
+        keys_spare_.reset();
+        pos_spare_.reset();
         refine_rounds = doubling_rounds = 0;
         for (auto& ev : downsweep_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
         downsweep_events.clear();
@@ -1035,6 +1074,7 @@ void Build::run(SufrB200Result* out) {
 
     // finish: lower-bound LCP marks left by prefix doubling (text order, on the unfiltered arrays), then the
     // suffix filter when it was not applied up front, then the N-run rule
+    if (doubling_rounds || (filter_active && !prefilter) || sliced) drop_wide();
     if (doubling_rounds && s) {
         if (!d_isa || s != n) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling ran on a partial suffix set");
         uint64_t chunks = div_up(n, kPlcpChunk);
@@ -1113,7 +1153,22 @@ void Build::run(SufrB200Result* out) {
             d_exc_val.reset();
         }
     }
-    if (index_bits_ == 64 && !compact) {
+    if (index_bits_ == 64 && !compact && wide_ok_) {
+        if (wide_m_) {
+            wide_patch_kernel<<<grid_for(wide_m_, 2), kBlock, 0, st()>>>(wide_m_, wide_slots_.get(), d_sa.get(), d_lcp.get(),
+                                                                       wide_sa_.get(), wide_lcp_.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+        }
+        sa64 = std::move(wide_sa_);
+        lcp64 = std::move(wide_lcp_);
+        wide_slots_.reset();
+        d_sa.reset();
+        d_lcp.reset();
+        d_sa_out = sa64.get();
+        d_lcp_out = lcp64.get();
+    } else if (index_bits_ == 64 && !compact) {
+        drop_wide();
         sa64 = dalloc<unsigned long long>(s);
         lcp64 = dalloc<unsigned long long>(s);
         if (s) {

@@ -981,7 +981,9 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
                                                               uint32_t* __restrict__ act_slot,
                                                               uint32_t* __restrict__ act_pos,
                                                               unsigned long long* __restrict__ act_count,
-                                                              uint64_t capacity) {
+                                                              uint64_t capacity,
+                                                              unsigned long long* __restrict__ sa64,
+                                                              unsigned long long* __restrict__ lcp64) {
     constexpr uint32_t RL = kFast2SmallGroup + 1;  // a run of RL records or more is "large"
     __shared__ uint64_t ka[kR0N], kb[kR0N];
     __shared__ uint32_t pa[kR0N], pb[kR0N];
@@ -1093,6 +1095,10 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
             apos[k] = pb[d];
             keys_t[d] = k0;
             pos_t[d] = apos[k];
+            if (sa64) {  // 64-bit device results: written here, later changes are patched in (Build::refine)
+                sa64[g0 + d] = apos[k];
+                lcp64[g0 + d] = out;
+            }
             if (is_large) atomicOr(&large[(g0 + d) >> 5], 1u << ((g0 + d) & 31));
             if (!head || next_same) act |= 1u << k;
         }
@@ -1132,7 +1138,8 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
 
 // Exact LCP of the boundaries the fast path could not read off the keys, from the FINAL suffix order.
 __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
-                                                           uint32_t* __restrict__ lcp) {
+                                                           uint32_t* __restrict__ lcp,
+                                                           unsigned long long* __restrict__ lcp64) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
     for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < s; j0 += stride) {
         uint32_t v[4];
@@ -1146,7 +1153,11 @@ __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t 
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const uint64_t j = j0 + u;
-            if (j < s && v[u] == kLcpFixup) lcp[j] = j ? (uint32_t)lcp_direct(ks, sa[j - 1], sa[j], 0) : 0u;
+            if (j < s && v[u] == kLcpFixup) {
+                const uint32_t l = j ? (uint32_t)lcp_direct(ks, sa[j - 1], sa[j], 0) : 0u;
+                lcp[j] = l;
+                if (lcp64) lcp64[j] = l;  // 64-bit results written early by round 0 (see Build::refine)
+            }
         }
     }
 }
@@ -1751,6 +1762,20 @@ __global__ void __launch_bounds__(kBlock) lcp_to_u8_kernel(const uint32_t* __res
             for (int u = 0; u < 16; u++)
                 if (j0 + u < s) out8[j0 + u] = (uint8_t)(packed[u >> 2] >> (8 * (u & 3)));
         }
+    }
+}
+
+// 64-bit results written early by round 0: copy the entries the refinement changed afterwards.
+__global__ void __launch_bounds__(kBlock) wide_patch_kernel(uint64_t m, const uint32_t* __restrict__ slots,
+                                                            const uint32_t* __restrict__ sa,
+                                                            const uint32_t* __restrict__ lcp,
+                                                            unsigned long long* __restrict__ sa64,
+                                                            unsigned long long* __restrict__ lcp64) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const uint32_t t = slots[i];
+        sa64[t] = sa[t];
+        lcp64[t] = lcp[t];
     }
 }
 

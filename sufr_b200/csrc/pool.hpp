@@ -26,6 +26,15 @@ class DevicePool {
         add_chunk(bytes);
     }
 
+    // How many allocations of `bytes` the free lists can serve without growing the pool.
+    size_t count_fits(size_t bytes) const {
+        bytes = round_up(bytes ? bytes : 1);
+        size_t k = 0;
+        for (auto& c : chunks_)
+            for (auto& f : c.free_list) k += f.second / bytes;
+        return k;
+    }
+
     void* alloc(size_t bytes) {
         bytes = round_up(bytes ? bytes : 1);
         for (int attempt = 0; attempt < 2; attempt++) {

@@ -385,6 +385,30 @@ def dna_with_rare(rng, n, rare=b"N%RYnacgt", rare_p=0.01, repeat_p=0.02, max_rep
     return bytes(out[:n])
 
 
+@pytest.mark.parametrize("flags", [dict(is_dna=True), dict(is_dna=True, ignore_softmask=True), dict(),
+                                   dict(is_dna=True, allow_ambiguity=True)])
+@pytest.mark.parametrize("deep", [False, True])
+def test_fast2_device_u64_results_written_early(S, flags, deep, monkeypatch):
+    """64-bit device results of the fast path are written by round 0 and patched where the refinement changes
+    them; prefix doubling, the post-sort filter and the N-run rule fall back to the widening pass."""
+    import torch
+    rng = random.Random(seed_of("early_wide", str(flags), deep))
+    text = dna_with_rare(rng, 120000) + (b"ACGGT" * 3000 if deep else b"") + b"$"
+    want = O.oracle_build(text, threads=4, **flags)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("SUFR_B200_DEBUG_NO_EARLY_WIDE", env)
+        r = S.build(S.SufrBuilderArgs(text=b"", **flags), index_bits=64, result_memory=S.MEM_DEVICE,
+                    device_text=(d_text.data_ptr(), d_text.numel()))
+        sa = r.sa_tensor().cpu().numpy().astype(np.uint64)
+        lcp = r.lcp_tensor().cpu().numpy().astype(np.uint64)
+        assert r.num_suffixes == want.num_suffixes
+        assert np.array_equal(sa, want.sa.astype(np.uint64))
+        assert np.array_equal(lcp, want.lcp.astype(np.uint64))
+        r.free()
+
+
 @pytest.mark.parametrize("n", [5000, 70000, 300000])
 @pytest.mark.parametrize("flags", [dict(is_dna=True), dict(is_dna=True, allow_ambiguity=True),
                                    dict(is_dna=True, ignore_softmask=True), dict()],
