@@ -1132,7 +1132,9 @@ void Build::run(SufrB200Result* out) {
     DevBuf<uint32_t> d_exc_idx, d_exc_val;
     uint64_t exc_count = 0;
     if (compact) {
-        const uint64_t capacity = s / 64 + 1024;
+        // LCP values >= 255 travel as (index, value) pairs and cost the host a random write each: worth it only
+        // while they are rare (a repetitive text takes the plain path)
+        const uint64_t capacity = s / 2048 + 1024;
         d_lcp8 = dalloc<uint8_t>(s + 16);
         d_exc_idx = dalloc<uint32_t>(capacity);
         d_exc_val = dalloc<uint32_t>(capacity);
@@ -1236,10 +1238,18 @@ void Build::run(SufrB200Result* out) {
             std::thread lcp_worker([=, &eidx, &eval]() {
                 if (bits == 64) host_widen(h8, (uint64_t*)lcp_out, s, threads);
                 else host_widen(h8, (uint32_t*)lcp_out, s, threads);
-                for (uint64_t e = 0; e < exc_count; e++) {
-                    if (bits == 64) ((uint64_t*)lcp_out)[eidx[e]] = eval[e];
-                    else ((uint32_t*)lcp_out)[eidx[e]] = eval[e];
+                // the exceptions arrive unordered (random writes into the result): spread them over the threads
+                std::vector<std::thread> pool;
+                for (int t = 0; t < threads; t++) {
+                    pool.emplace_back([=, &eidx, &eval]() {
+                        const uint64_t lo = exc_count * (uint64_t)t / threads, hi = exc_count * (uint64_t)(t + 1) / threads;
+                        for (uint64_t e = lo; e < hi; e++) {
+                            if (bits == 64) ((uint64_t*)lcp_out)[eidx[e]] = eval[e];
+                            else ((uint32_t*)lcp_out)[eidx[e]] = eval[e];
+                        }
+                    });
                 }
+                for (auto& th : pool) th.join();
             });
             struct Joiner {  // a CUDA error below must not leave the worker running on freed buffers
                 std::thread& t;

@@ -409,6 +409,33 @@ def test_fast2_device_u64_results_written_early(S, flags, deep, monkeypatch):
         r.free()
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_fast2_sharded_device_u64_results(S, world):
+    """The multi-GPU bench path: fast-path shards with 64-bit results left on the device, seams repaired there."""
+    import torch
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    rng = random.Random(seed_of("sharded_wide", world))
+    text = dna_with_rare(rng, 200000) + b"$"
+    want = O.oracle_build(text, is_dna=True, threads=4)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    shards = [S.build(S.SufrBuilderArgs(text=b"", is_dna=True), index_bits=64, result_memory=S.MEM_DEVICE,
+                      device_text=(d_text.data_ptr(), d_text.numel()), rank=r, world_size=world) for r in range(world)]
+    meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+    offs, total = shard_layout(meta)
+    assert total == want.num_suffixes
+    for r, s in enumerate(shards):
+        s.set_shard_layout(offs[r], total)
+        prev = previous_last_suffix(meta, r)
+        if prev is not None and s.num_suffixes:
+            s.patch_seam(prev)
+    sa = np.concatenate([s.sa_tensor().cpu().numpy().astype(np.uint64) for s in shards if s.num_suffixes])
+    lcp = np.concatenate([s.lcp_tensor().cpu().numpy().astype(np.uint64) for s in shards if s.num_suffixes])
+    assert np.array_equal(sa, want.sa.astype(np.uint64))
+    assert np.array_equal(lcp, want.lcp.astype(np.uint64))
+    for s in shards:
+        s.free()
+
+
 @pytest.mark.parametrize("n", [5000, 70000, 300000])
 @pytest.mark.parametrize("flags", [dict(is_dna=True), dict(is_dna=True, allow_ambiguity=True),
                                    dict(is_dna=True, ignore_softmask=True), dict()],
