@@ -310,13 +310,13 @@ def main():
 
 
 TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on the "
-                  "200 Mbp workload (profiles/r1_v5_downsweep_raw.csv: 2.785 GB + 2.711 GB for 4.800 GB "
+                  "200 Mbp workload (profiles/r1_v7_downsweep_raw.csv: 2.781 GB + 2.686 GB for 4.800 GB "
                   "algorithmic), scaled to this launch's element count")
 
 
 def traffic_estimate(algorithmic_bytes):
     """DRAM bytes per launch of the dominant kernel (see TRAFFIC_SOURCE)."""
-    return algorithmic_bytes * (2.785239 + 2.710943) / 4.800000576
+    return algorithmic_bytes * (2.781094 + 2.685538) / 4.800000576
 
 
 def run_repetitive(args, S, ctx, dev):
