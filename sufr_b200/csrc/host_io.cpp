@@ -9,6 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -170,69 +174,203 @@ void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
 // ------------------------------------------------------------------ FASTA / FASTQ ingest (util.rs:51-89)
 // The reference delegates parsing to needletail 0.6 (not vendored).  This follows its documented
 // behaviour for plain-text input: FASTA records may span lines, FASTQ records are 4 lines, '\r' is
-// stripped, the id is the header up to the first whitespace.
+// stripped at line ends, the id is the header up to the first whitespace.
+//
+// FASTA is parsed by all host cores: the file is read with parallel preads, cut into slices at line starts, and
+// every slice is handled in two passes (count, then write at its final offset), so a 3 Gbp genome is ingested at
+// memory speed instead of by one core.  FASTQ (line roles depend on the line number) stays serial.
+namespace {
+
+struct FileData {
+    char* p = nullptr;
+    size_t n = 0;
+    ~FileData() { free(p); }
+};
+
+int ingest_threads(size_t bytes) {
+    size_t t = std::thread::hardware_concurrency();
+    if (t == 0) t = 1;
+    if (t > 32) t = 32;
+    size_t by_size = bytes / (4u << 20) + 1;  // no point in a thread per few MB
+    return (int)std::min(t, by_size);
+}
+
+template <typename F>
+void parallel_for(int threads, F f) {
+    if (threads <= 1) { f(0); return; }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(threads);
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t]() { try { f(t); } catch (...) { err[t] = std::current_exception(); } });
+    for (auto& th : pool) th.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+}
+
+void load_file(const char* path, FileData& d) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+        d.n = (size_t)st.st_size;
+        d.p = (char*)malloc(d.n);
+        if (!d.p) { close(fd); throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, std::string(path) + ": out of host memory"); }
+        const int T = ingest_threads(d.n);
+        try {
+            parallel_for(T, [&](int t) {
+                size_t lo = d.n * (size_t)t / T, hi = d.n * (size_t)(t + 1) / T;
+                while (lo < hi) {
+                    ssize_t got = pread(fd, d.p + lo, std::min<size_t>(hi - lo, 1u << 30), (off_t)lo);
+                    if (got < 0 && errno == EINTR) continue;
+                    if (got <= 0) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": " + (got < 0 ? strerror(errno) : "short read"));
+                    lo += (size_t)got;
+                }
+            });
+        } catch (...) { close(fd); throw; }
+        close(fd);
+        return;
+    }
+    // pipes and other non-regular files: sequential read
+    std::string data;
+    char buf[1 << 16];
+    ssize_t got;
+    while ((got = read(fd, buf, sizeof(buf))) != 0) {
+        if (got < 0) { if (errno == EINTR) continue; close(fd); throw Error(SUFR_B200_ERR_IO, std::string(path) + ": " + strerror(errno)); }
+        data.append(buf, (size_t)got);
+    }
+    close(fd);
+    d.n = data.size();
+    d.p = (char*)malloc(std::max<size_t>(1, d.n));
+    memcpy(d.p, data.data(), d.n);
+}
+
+// one line [b, e) starting at `pos` (e excludes "\n" and a "\r" right before it); advances pos behind the line
+inline bool next_line(const char* data, size_t n, size_t& pos, size_t& b, size_t& e) {
+    if (pos >= n) return false;
+    b = pos;
+    const void* nl = memchr(data + pos, '\n', n - pos);
+    e = nl ? (size_t)((const char*)nl - data) : n;
+    pos = e + 1;
+    if (e > b && data[e - 1] == '\r') e--;
+    return true;
+}
+
+std::string record_name(const char* data, size_t hb, size_t he, uint64_t ordinal) {  // util.rs:73-76
+    size_t s = hb;
+    while (s < he && isspace((unsigned char)data[s])) s++;
+    size_t e = s;
+    while (e < he && !isspace((unsigned char)data[e])) e++;
+    return e > s ? std::string(data + s, e - s) : std::to_string(ordinal + 1);
+}
+
+struct Slice {
+    size_t lo = 0, hi = 0;        // lines that START in [lo, hi)
+    uint64_t seq_bytes = 0;       // sequence bytes of the slice
+    uint64_t headers = 0;
+    uint64_t out_off = 0;         // where the slice's output starts
+    uint64_t first_record = 0;    // ordinal of the slice's first header
+    std::vector<uint64_t> starts;
+    std::vector<std::pair<size_t, size_t>> header_lines;
+};
+
+}  // namespace
+
 void read_sequence_file(const char* path, uint8_t delim, SufrB200Sequences* out) {
     memset(out, 0, sizeof(*out));
-    FILE* f = fopen(path, "rb");
-    if (!f) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": " + strerror(errno));
-    std::string data;
-    {
-        char buf[1 << 16];
-        size_t got;
-        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, got);
-        fclose(f);
-    }
-    if (data.empty()) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": empty input (no FASTA/FASTQ record)");
+    FileData file;
+    load_file(path, file);
+    const char* data = file.p;
+    const size_t n = file.n;
+    if (n == 0) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": empty input (no FASTA/FASTQ record)");
     if (data[0] != '>' && data[0] != '@')
         throw Error(SUFR_B200_ERR_IO, std::string(path) + ": not a FASTA/FASTQ file");
 
-    std::vector<uint8_t> seq;
-    seq.reserve(data.size() + 1);
     std::vector<uint64_t> starts;
     std::vector<std::string> names;
-    size_t pos = 0;
-    const size_t n = data.size();
-    auto next_line = [&](size_t& b, size_t& e) -> bool {
-        if (pos >= n) return false;
-        b = pos;
-        const void* nl = memchr(data.data() + pos, '\n', n - pos);
-        e = nl ? (size_t)((const char*)nl - data.data()) : n;
-        pos = e + 1;
-        if (e > b && data[e - 1] == '\r') e--;
-        return true;
-    };
-    uint64_t i = 0;
-    auto begin_record = [&](size_t hb, size_t he) {
-        if (i > 0) seq.push_back(delim);     // util.rs:62-64
-        starts.push_back(seq.size());        // util.rs:67
-        i += 1;
-        size_t s = hb;
-        while (s < he && isspace((unsigned char)data[s])) s++;
-        size_t e = s;
-        while (e < he && !isspace((unsigned char)data[e])) e++;
-        names.push_back(e > s ? data.substr(s, e - s) : std::to_string(i + 1));  // util.rs:73-76
-    };
-    size_t b, e;
+    uint8_t* seq = nullptr;
+    uint64_t seq_len = 0;
+
     if (data[0] == '>') {
-        while (next_line(b, e)) {
-            if (e > b && data[b] == '>') begin_record(b + 1, e);
-            else seq.insert(seq.end(), data.begin() + b, data.begin() + e);
+        const int T = ingest_threads(n);
+        std::vector<Slice> sl(T);
+        for (int t = 0; t < T; t++) {  // slice boundaries moved forward to the next line start
+            size_t lo = n * (size_t)t / T;
+            if (t > 0 && lo > 0 && data[lo - 1] != '\n') {
+                const void* nl = memchr(data + lo, '\n', n - lo);
+                lo = nl ? (size_t)((const char*)nl - data) + 1 : n;
+            }
+            sl[t].lo = lo;
+            if (t > 0) sl[t - 1].hi = lo;
+        }
+        sl[T - 1].hi = n;
+        for (int t = 1; t < T; t++) if (sl[t].lo < sl[t - 1].lo) sl[t].lo = sl[t - 1].lo;  // (monotone by construction)
+        parallel_for(T, [&](int t) {  // pass 1: sizes
+            Slice& c = sl[t];
+            size_t pos = c.lo, b, e;
+            while (pos < c.hi && next_line(data, n, pos, b, e)) {
+                if (e > b && data[b] == '>') { c.headers++; c.header_lines.push_back({b + 1, e}); }
+                else c.seq_bytes += e - b;
+            }
+        });
+        uint64_t off = 0, rec = 0;
+        for (int t = 0; t < T; t++) {
+            sl[t].out_off = off;
+            sl[t].first_record = rec;
+            off += sl[t].seq_bytes + sl[t].headers;  // one delimiter per header ...
+            rec += sl[t].headers;
+        }
+        seq_len = off - 1 + 1;  // ... except the first record (util.rs:62-64), plus the sentinel
+        seq = (uint8_t*)malloc(seq_len);
+        if (!seq) throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, std::string(path) + ": out of host memory");
+        parallel_for(T, [&](int t) {  // pass 2: write every slice at its final offset
+            Slice& c = sl[t];
+            // the global first header writes no delimiter, so everything behind it sits one byte earlier
+            uint64_t o = c.out_off - (t > 0 ? 1 : 0);
+            uint64_t ordinal = c.first_record;
+            size_t pos = c.lo, b, e;
+            while (pos < c.hi && next_line(data, n, pos, b, e)) {
+                if (e > b && data[b] == '>') {
+                    if (ordinal > 0) seq[o++] = delim;
+                    c.starts.push_back(o);
+                    ordinal++;
+                } else {
+                    memcpy(seq + o, data + b, e - b);
+                    o += e - b;
+                }
+            }
+        });
+        seq[seq_len - 1] = '$';  // SENTINEL_CHARACTER, types.rs:20 / util.rs:82
+        for (int t = 0; t < T; t++) {
+            uint64_t ordinal = sl[t].first_record;
+            for (size_t k = 0; k < sl[t].starts.size(); k++) {
+                starts.push_back(sl[t].starts[k]);
+                ordinal++;
+                names.push_back(record_name(data, sl[t].header_lines[k].first, sl[t].header_lines[k].second, ordinal));
+            }
         }
     } else {
-        while (next_line(b, e)) {
+        std::vector<uint8_t> buf;
+        buf.reserve(n / 2 + 1);
+        size_t pos = 0, b, e;
+        uint64_t i = 0;
+        while (next_line(data, n, pos, b, e)) {
             if (e == b) continue;
-            begin_record(b + 1, e);
+            if (i > 0) buf.push_back(delim);
+            starts.push_back(buf.size());
+            i += 1;
+            names.push_back(record_name(data, b + 1, e, i));
             size_t sb, se, xb, xe;
-            if (!next_line(sb, se) || !next_line(xb, xe) || !next_line(xb, xe))
+            if (!next_line(data, n, pos, sb, se) || !next_line(data, n, pos, xb, xe) || !next_line(data, n, pos, xb, xe))
                 throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated FASTQ record");
-            seq.insert(seq.end(), data.begin() + sb, data.begin() + se);
+            buf.insert(buf.end(), data + sb, data + se);
         }
+        buf.push_back('$');
+        seq_len = buf.size();
+        seq = (uint8_t*)malloc(seq_len);
+        memcpy(seq, buf.data(), seq_len);
     }
-    seq.push_back('$');  // SENTINEL_CHARACTER, types.rs:20 / util.rs:82
 
-    out->seq_len = seq.size();
-    out->seq = (uint8_t*)malloc(seq.size());
-    memcpy(out->seq, seq.data(), seq.size());
+    out->seq_len = seq_len;
+    out->seq = seq;
     out->num_sequences = starts.size();
     out->start_positions = (uint64_t*)malloc(std::max<size_t>(1, starts.size()) * 8);
     out->sequence_names = (char**)malloc(std::max<size_t>(1, names.size()) * sizeof(char*));

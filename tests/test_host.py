@@ -134,6 +134,39 @@ def test_read_sequence_file_kat_and_errors(S, tmp_path):
     assert (d.seq, d.start_positions, d.sequence_names) == (b"ACGT%TT$", [0, 5], ["a", "c"])
 
 
+@pytest.mark.parametrize("seed,records,crlf,final_newline", [(1, 3, False, True), (2, 2000, True, False),
+                                                             (3, 40, False, False)])
+def test_parallel_fasta_ingest_matches_serial_restatement(S, tmp_path, seed, records, crlf, final_newline):
+    """Files of tens of MB are read and parsed by several threads (slices cut at line starts): same text,
+    starts and names as the serial restatement of util.rs:51-89, whatever the line structure."""
+    import random
+    rng = random.Random(seed)
+    total = 40_000_000
+    eol = b"\r\n" if crlf else b"\n"
+    parts = []
+    for r in range(records):
+        parts.append(b">rec%d some description" % r + eol)
+        left = total // records
+        body = bytes(rng.choices(b"ACGTN", k=1000)) * (left // 1000 + 1)
+        pos = 0
+        while pos < left:
+            w = rng.choice([60, 61, 80, 1, 200, 100000])
+            parts.append(body[pos:pos + min(w, left - pos)] + eol)
+            pos += w
+            if rng.random() < 0.01:
+                parts.append(eol)  # blank line inside a record
+    blob = b"".join(parts)
+    if not final_newline:
+        blob = blob.rstrip(b"\r\n")
+    fa = tmp_path / "big.fa"
+    fa.write_bytes(blob)
+    a = S.read_sequence_file(fa, b"%")
+    b = O.read_sequence_file(fa, b"%")
+    assert a.start_positions == b.start_positions
+    assert a.sequence_names == b.sequence_names
+    assert a.seq == b.seq
+
+
 def _host_result(S, o, shard=None):
     """A SufrB200Result in host memory filled from oracle arrays (exercises the writer without a GPU)."""
     from sufr_b200 import _lib
