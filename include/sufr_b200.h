@@ -140,8 +140,12 @@ int sufr_b200_patch_seam(SufrB200Ctx* ctx, const SufrB200Args* args, SufrB200Res
 int sufr_b200_write(const SufrB200Args* args, const SufrB200Result* result);
 
 /* -- create: SufrBuilder::new as a single call (build on `device`, then write args->path or
- *    "out.sufr").  The result is returned like the reference returns the builder struct;
- *    free it with sufr_b200_result_free(NULL, out).  `out` may be NULL. */
+ *    "out.sufr").  The suffix and LCP arrays stream from device memory into the file through a ring
+ *    of pinned buffers (copy and pwrite overlap; no host copy of them is allocated), so the result is
+ *    what the reference's builder struct holds after `new` (sufr_builder.rs:38-89): counts, the
+ *    transformed text, n_ranges -- `sa` and `lcp` are NULL, they are in the file.  timings.d2h_ms is
+ *    the wall time of that streaming write.  Free with sufr_b200_result_free(NULL, out).
+ *    `out` may be NULL. */
 int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out);
 
 /* -- helpers shared with the host-side mirror ---------------------------------------------- */

@@ -11,8 +11,15 @@
 //   finish   N-run tie rule, suffix filter, widen     sufr_builder.rs:305-307, :446-449
 //
 // The oracle (oracle/) is never linked or called from here.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -93,6 +100,7 @@ struct Ctx {
 struct ResultOwner {
     Ctx* ctx = nullptr;          // device buffers go back to this pool
     bool owns_ctx = false;       // sufr_b200_create made a private context
+    bool text_malloc = false;    // host text from malloc (sufr_b200_create), not from the pinned cache
     int memory = SUFR_B200_MEM_HOST;
     void* text = nullptr;
     void* sa = nullptr;
@@ -1340,7 +1348,8 @@ static void free_owner(ResultOwner* o) {
         if (o->sa) o->ctx->pinned.put(o->sa);
         if (o->lcp) o->ctx->pinned.put(o->lcp);
     } else {
-        if (o->text) cudaFreeHost(o->text);
+        if (o->text && o->text_malloc) free(o->text);
+        else if (o->text) cudaFreeHost(o->text);
         if (o->sa) cudaFreeHost(o->sa);
         if (o->lcp) cudaFreeHost(o->lcp);
     }
@@ -1367,6 +1376,155 @@ static int guarded(F&& f) {
         g_last_error = e.what();
         return SUFR_B200_ERR_INTERNAL;
     }
+}
+
+// sufr_b200_create: the sections of the file go from device memory to the file through a small ring of pinned
+// buffers -- the device->host copy of one chunk overlaps the pwrite of the previous ones, and no host copy of the
+// suffix / LCP arrays is ever allocated (page-locking 2 * s * sizeof(T) bytes costs seconds by itself).
+class StreamWriter {
+   public:
+    StreamWriter(int fd, const std::string& path, int device, cudaStream_t stream, size_t slot_bytes = 64u << 20, int nslots = 6,
+                 int nworkers = 4)
+        : fd_(fd), path_(path), device_(device), stream_(stream), slot_bytes_(slot_bytes) {
+        for (int i = 0; i < nslots; i++) {
+            Slot sl;
+            SUFR_CUDA_CHECK(cudaMallocHost(&sl.buf, slot_bytes_));
+            SUFR_CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+            slots_.push_back(sl);
+            free_.push_back(i);
+        }
+        for (int i = 0; i < nworkers; i++) workers_.emplace_back([this] { work(); });
+    }
+    ~StreamWriter() {
+        try { finish(); } catch (...) {}
+        for (auto& sl : slots_) {
+            cudaFreeHost(sl.buf);
+            cudaEventDestroy(sl.ev);
+        }
+    }
+    // Queue `len` bytes of device memory for file offset `off`; `host_copy` (optional) also receives them.
+    void submit(const void* dev, size_t len, uint64_t off, uint8_t* host_copy = nullptr) {
+        const char* p = (const char*)dev;
+        while (len) {
+            const size_t chunk = std::min(len, slot_bytes_);
+            int slot;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_free_.wait(lock, [&] { return !free_.empty() || err_; });
+                if (err_) std::rethrow_exception(err_);
+                slot = free_.front();
+                free_.pop_front();
+            }
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(slots_[slot].buf, p, chunk, cudaMemcpyDeviceToHost, stream_));
+            SUFR_CUDA_CHECK(cudaEventRecord(slots_[slot].ev, stream_));
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                jobs_.push_back({slot, chunk, off, host_copy});
+            }
+            cv_work_.notify_one();
+            p += chunk;
+            off += chunk;
+            if (host_copy) host_copy += chunk;
+            len -= chunk;
+            bytes_ += chunk;
+        }
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            if (done_) return;
+            done_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto& t : workers_) t.join();
+        workers_.clear();
+        if (err_) std::rethrow_exception(err_);
+    }
+    uint64_t bytes() const { return bytes_; }
+
+   private:
+    struct Slot { void* buf; cudaEvent_t ev; };
+    struct Job { int slot; size_t len; uint64_t off; uint8_t* host_copy; };
+    void work() {
+        cudaSetDevice(device_);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_work_.wait(lock, [&] { return !jobs_.empty() || done_; });
+                if (jobs_.empty()) return;
+                j = jobs_.front();
+                jobs_.pop_front();
+            }
+            try {
+                cudaError_t e = cudaEventSynchronize(slots_[j.slot].ev);
+                if (e != cudaSuccess) throw Error(100 + (int)e, std::string("CUDA error in the file writer: ") + cudaGetErrorString(e));
+                if (j.host_copy) memcpy(j.host_copy, slots_[j.slot].buf, j.len);
+                pwrite_all(fd_, slots_[j.slot].buf, j.len, j.off, path_);
+            } catch (...) {
+                std::lock_guard<std::mutex> lock(mu_);
+                if (!err_) err_ = std::current_exception();
+            }
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                free_.push_back(j.slot);
+            }
+            cv_free_.notify_one();
+        }
+    }
+    int fd_;
+    std::string path_;
+    int device_;
+    cudaStream_t stream_;
+    size_t slot_bytes_;
+    std::vector<Slot> slots_;
+    std::deque<int> free_;
+    std::deque<Job> jobs_;
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_free_, cv_work_;
+    bool done_ = false;
+    std::exception_ptr err_;
+    uint64_t bytes_ = 0;
+};
+
+// Writes the file of a DEVICE result (sufr_builder.rs:817-918) and returns the transformed text in `host_text`
+// (malloc; what SufrBuilder.text holds after `new`).
+static void stream_result_to_file(Ctx& ctx, const SufrB200Args& args, const SufrB200Result& r, uint8_t** host_text) {
+    const std::string path = args.path ? args.path : "out.sufr";  // sufr_builder.rs:215
+    const size_t w = r.index_bits / 8;
+    const SufrFrame f = make_sufr_frame(args, r.index_bits, r.text_len, r.total_suffixes);
+    const bool sharded = args.world_size > 1;
+    const bool leader = !sharded || args.rank == 0;
+    int fd = open(path.c_str(), O_WRONLY | O_CREAT | (sharded ? 0 : O_TRUNC), 0644);
+    if (fd < 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));  // sufr_builder.rs:820
+    uint8_t* text = nullptr;
+    try {
+        if (leader) {  // ranks > 0 of a sharded build neither write nor return the text
+            text = (uint8_t*)malloc(std::max<uint64_t>(1, r.text_len));
+            if (!text) throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, "out of host memory for the transformed text");
+        }
+        {
+            const int hw = (int)std::thread::hardware_concurrency();
+            StreamWriter sw(fd, path, ctx.device, ctx.stream, 64u << 20, 8, std::max(2, std::min(8, hw / 2)));
+            if (leader) {
+                pwrite_all(fd, f.head.data(), f.head.size(), 0, path);
+                pwrite_all(fd, f.tail.data(), f.tail.size(), f.names_pos, path);
+                if (sharded && ftruncate(fd, (off_t)(f.names_pos + f.tail.size())) != 0)
+                    throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
+            }
+            if (leader) sw.submit(r.text, r.text_len, f.text_pos, text);
+            sw.submit(r.sa, r.num_suffixes * w, f.sa_pos + r.shard_offset * w);
+            sw.submit(r.lcp, r.num_suffixes * w, f.lcp_pos + r.shard_offset * w);
+            sw.finish();
+        }
+    } catch (...) {
+        close(fd);
+        free(text);
+        throw;
+    }
+    if (close(fd) != 0) { free(text); throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno)); }
+    if (host_text) *host_text = text; else free(text);
 }
 
 static Ctx* make_ctx(int device) {
@@ -1577,25 +1735,50 @@ int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out) 
     int rc = guarded([&] {
         if (!args) throw Error(SUFR_B200_ERR_ARGUMENT, "args is NULL");
         std::unique_ptr<Ctx> ctx(make_ctx(device));
+        SufrB200Result dev;
+        memset(&dev, 0, sizeof(dev));
+        auto teardown = [&] {
+            if (dev.owner) free_owner(static_cast<ResultOwner*>(dev.owner));
+            dev.owner = nullptr;
+            cudaStreamSynchronize(ctx->stream);
+            ctx->pinned.sizes.clear();
+            ctx->pinned.release();
+            ctx->pool.release_all();
+            cudaStreamDestroy(ctx->stream);
+        };
         try {
             {
                 std::lock_guard<std::mutex> lock(ctx->mu);
-                Build b(*ctx, *args, 0, SUFR_B200_MEM_HOST, SUFR_B200_MEM_HOST);
-                b.run(res);
+                Build b(*ctx, *args, 0, SUFR_B200_MEM_HOST, SUFR_B200_MEM_DEVICE);
+                b.run(&dev);
             }
-            write_sufr_file(*args, *res);
+            // the suffix and LCP arrays go straight from device memory into the file
+            uint8_t* host_text = nullptr;
+            const auto w0 = std::chrono::steady_clock::now();
+            stream_result_to_file(*ctx, *args, dev, &host_text);
+            const double write_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+            auto owner = std::make_unique<ResultOwner>();
+            owner->memory = SUFR_B200_MEM_HOST;
+            owner->text = host_text;
+            owner->text_malloc = true;
+            if (dev.num_n_ranges) {
+                owner->n_ranges = (uint64_t*)malloc(dev.num_n_ranges * 16);
+                memcpy(owner->n_ranges, dev.n_ranges, dev.num_n_ranges * 16);
+            }
+            *res = dev;
+            res->memory = SUFR_B200_MEM_HOST;
+            res->text = host_text;
+            res->sa = nullptr;   // in the file, like the reference's builder struct (sufr_builder.rs:38-89)
+            res->lcp = nullptr;
+            res->n_ranges = owner->n_ranges;
+            res->timings.d2h_ms = write_ms;  // device -> host -> file, overlapped
+            res->d2h_bytes = (host_text ? dev.text_len : 0) + 2 * dev.num_suffixes * (dev.index_bits / 8);
+            res->owner = owner.release();
         } catch (...) {
-            cudaStreamSynchronize(ctx->stream);
-            ctx->pool.release_all();
-            cudaStreamDestroy(ctx->stream);
+            teardown();
             throw;
         }
-        // host result does not need the context any more (its pinned buffers are freed with cudaFreeHost)
-        static_cast<ResultOwner*>(res->owner)->ctx = nullptr;
-        ctx->pinned.sizes.clear();
-        ctx->pinned.release();
-        ctx->pool.release_all();
-        cudaStreamDestroy(ctx->stream);
+        teardown();
     });
     if (rc == SUFR_B200_OK && !out) sufr_b200_result_free(nullptr, &local);
     return rc;

@@ -48,43 +48,12 @@ uint64_t lcp_full_offset(uint64_t lcp, const SeedMaskInfo& m) {
     return offset + 1;
 }
 
-static bool in_n_run(const uint64_t* r, uint64_t k, uint64_t p, uint64_t& end) {
-    uint64_t lo = 0, hi = k;
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) / 2;
-        if (r[2 * mid] <= p && p < r[2 * mid + 1]) { end = r[2 * mid + 1]; return true; }
-        if (r[2 * mid] < p) lo = mid + 1; else hi = mid;
-    }
-    return false;
-}
-
-uint64_t host_pair_lcp(const uint8_t* text, uint64_t n, uint64_t a, uint64_t b, const SeedMaskInfo* mask, uint64_t q,
-                       const uint64_t* n_ranges, uint64_t num_n_ranges) {
-    if (mask) {
-        uint64_t c = 0;
-        for (uint64_t k = 0; k < mask->positions.size(); k++) {
-            uint64_t x = a + mask->positions[k], y = b + mask->positions[k];
-            if (x >= n || y >= n || text[x] != text[y]) break;
-            c++;
-        }
-        return c;
-    }
-    uint64_t ea, eb;
-    if (num_n_ranges && in_n_run(n_ranges, num_n_ranges, a, ea) && in_n_run(n_ranges, num_n_ranges, b, eb))
-        return std::min(ea - a, eb - b);
-    uint64_t lim = std::min(n - a, n - b);
-    if (q && q < lim) lim = q;
-    uint64_t c = 0;
-    while (c < lim && text[a + c] == text[b + c]) c++;
-    return c;
-}
-
 // ------------------------------------------------------------------ `.sufr` writer
 static void put_u64(std::vector<uint8_t>& out, uint64_t v) {  // util.rs:138-151
     for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i)));
 }
 
-static void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const std::string& path) {
+void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const std::string& path) {
     const char* p = (const char*)buf;
     while (len) {
         size_t chunk = len > (1u << 30) ? (1u << 30) : len;
@@ -99,24 +68,24 @@ static void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const 
     }
 }
 
-void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
-    const std::string path = args.path ? args.path : "out.sufr";  // sufr_builder.rs:215
-    const size_t w = r.index_bits / 8;
+SufrFrame make_sufr_frame(const SufrB200Args& args, uint32_t index_bits, uint64_t text_len, uint64_t total_suffixes) {
+    SufrFrame f;
+    const size_t w = index_bits / 8;
     SeedMaskInfo mask;
     const bool has_mask = args.seed_mask && parse_seed_mask(args.seed_mask, mask);
 
     // header (sufr_builder.rs:826-867); all integers little-endian
-    std::vector<uint8_t> head;
+    std::vector<uint8_t>& head = f.head;
     head.push_back(6);  // OUTFILE_VERSION, types.rs:16
     head.push_back(args.is_dna ? 1 : 0);
     head.push_back(args.allow_ambiguity ? 1 : 0);
     head.push_back(args.ignore_softmask ? 1 : 0);
-    put_u64(head, r.text_len);
+    put_u64(head, text_len);
     const size_t locs_pos = head.size();
     put_u64(head, 0);
     put_u64(head, 0);
     put_u64(head, 0);
-    put_u64(head, r.total_suffixes);
+    put_u64(head, total_suffixes);
     put_u64(head, has_mask ? 0 : (args.has_max_query_len ? args.max_query_len : 0));
     put_u64(head, args.num_sequences);
     for (uint64_t i = 0; i < args.num_sequences; i++) {
@@ -129,26 +98,35 @@ void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
     } else {
         put_u64(head, 0);
     }
-    const uint64_t text_pos = head.size();
-    const uint64_t sa_pos = text_pos + r.text_len;
-    const uint64_t lcp_pos = sa_pos + r.total_suffixes * w;
-    const uint64_t names_pos = lcp_pos + r.total_suffixes * w;
+    f.text_pos = head.size();
+    f.sa_pos = f.text_pos + text_len;
+    f.lcp_pos = f.sa_pos + total_suffixes * w;
+    f.names_pos = f.lcp_pos + total_suffixes * w;
     {
         std::vector<uint8_t> locs;
-        put_u64(locs, text_pos);
-        put_u64(locs, sa_pos);
-        put_u64(locs, lcp_pos);
+        put_u64(locs, f.text_pos);
+        put_u64(locs, f.sa_pos);
+        put_u64(locs, f.lcp_pos);
         memcpy(head.data() + locs_pos, locs.data(), locs.size());
     }
     // bincode 1.3 Vec<String>: u64 count, then per string u64 length + bytes (sufr_builder.rs:909)
-    std::vector<uint8_t> tail;
-    put_u64(tail, args.num_sequences);
+    put_u64(f.tail, args.num_sequences);
     for (uint64_t i = 0; i < args.num_sequences; i++) {
         const char* nm = args.sequence_names ? args.sequence_names[i] : "";
         size_t len = strlen(nm);
-        put_u64(tail, len);
-        tail.insert(tail.end(), nm, nm + len);
+        put_u64(f.tail, len);
+        f.tail.insert(f.tail.end(), nm, nm + len);
     }
+    return f;
+}
+
+void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
+    const std::string path = args.path ? args.path : "out.sufr";  // sufr_builder.rs:215
+    const size_t w = r.index_bits / 8;
+    const SufrFrame f = make_sufr_frame(args, r.index_bits, r.text_len, r.total_suffixes);
+    const std::vector<uint8_t>& head = f.head;
+    const std::vector<uint8_t>& tail = f.tail;
+    const uint64_t text_pos = f.text_pos, sa_pos = f.sa_pos, lcp_pos = f.lcp_pos, names_pos = f.names_pos;
 
     const bool sharded = args.world_size > 1;
     const bool leader = !sharded || args.rank == 0;

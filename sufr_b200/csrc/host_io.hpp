@@ -18,13 +18,17 @@ struct SeedMaskInfo {
 bool parse_seed_mask(const char* mask, SeedMaskInfo& out);
 uint64_t lcp_full_offset(uint64_t lcp, const SeedMaskInfo& m);  // util.rs:19-37
 
-// LCP of the pair (a, b) under the sort's own rules, on the transformed text (seam repair,
-// sufr_builder.rs:893-902).  `mask` may be NULL, `q` = max_query_len or 0.
-uint64_t host_pair_lcp(const uint8_t* text, uint64_t n, uint64_t a, uint64_t b, const SeedMaskInfo* mask, uint64_t q,
-                       const uint64_t* n_ranges, uint64_t num_n_ranges);
-
 // sufr_builder.rs:817-918
 void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r);
+
+// The parts of a version-6 `.sufr` file around the three big sections (sufr_builder.rs:826-867, :909).
+struct SufrFrame {
+    std::vector<uint8_t> head;  // everything before the text
+    std::vector<uint8_t> tail;  // bincode Vec<String> of the sequence names
+    uint64_t text_pos = 0, sa_pos = 0, lcp_pos = 0, names_pos = 0;
+};
+SufrFrame make_sufr_frame(const SufrB200Args& args, uint32_t index_bits, uint64_t text_len, uint64_t total_suffixes);
+void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const std::string& path);
 
 // util.rs:51-89
 void read_sequence_file(const char* path, uint8_t delim, SufrB200Sequences* out);
