@@ -561,7 +561,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             pos_a = dalloc<uint32_t>(capacity);
             SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
             if (n) {
-                if (ks.fast2 && !getenv("SUFR_B200_DEBUG_OLD_SELECT"))
+                if (ks.fast2)
                     select_fast2_kernel<<<grid_for(n, 32), kBlock, 0, st()>>>(ks, n, lo, hi, prefilter ? 1 : 0, keys_a.get(),
                                                                             pos_a.get(), d_cnt.get(), capacity);
                 else
@@ -670,21 +670,12 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     int word = fast2 ? -1 : 0;
     int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
     DevBuf<uint32_t> large;  // fast path: members of large groups that the register sort left alone
-    const bool fused0 = fast2 && !getenv("SUFR_B200_DEBUG_UNFUSED_ROUND0");
     if (fast2) {
         large = dalloc<uint32_t>(r0n / 32 + 1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(large.get(), 0, (r0n / 32 + 1) * 4, st()));
-        if (!fused0) {
-            fast2_group_sort_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get());
-            SUFR_KERNEL_CHECK();
-            launched();
-        }
     }
-    if (!fused0) {
-        keys_spare_.reset();
-        pos_spare_.reset();
-    }
-    ViewAll v0{fused0 ? keys_spare_.get() : keys_sorted.get(), fused0 ? pos_spare_.get() : d_sa.get(),
+    // the fast path's round 0 is out of place: the ordered records land in the sort's ping-pong partners
+    ViewAll v0{fast2 ? keys_spare_.get() : keys_sorted.get(), fast2 ? pos_spare_.get() : d_sa.get(),
                fast2 ? large.get() : nullptr};
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, pos, seg;
@@ -695,7 +686,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         auto act_pos = dalloc<uint32_t>(capacity);
         auto d_cnt = dalloc<unsigned long long>(1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
-        if (fused0) {
+        if (fast2) {
             drop_wide();
             if (index_bits_ == 64 && result_memory_ == SUFR_B200_MEM_DEVICE && !args.allow_ambiguity &&
                 !getenv("SUFR_B200_DEBUG_NO_EARLY_WIDE")) {
@@ -713,10 +704,6 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                                                                       pos_spare_.get(), r0n, large.get(), d_lcp.get(),
                                                                       act_slot.get(), act_pos.get(), d_cnt.get(), capacity,
                                                                       wide_sa_.get(), wide_lcp_.get());
-        } else if (fast2) {
-            resolve0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, large.get(),
-                                                                        d_lcp.get(), act_slot.get(), act_pos.get(),
-                                                                        d_cnt.get(), capacity);
         } else {
             resolve0_append_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks, final_word,
                                                                          d_lcp.get(), act_slot.get(), act_pos.get(),
@@ -724,7 +711,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         }
         SUFR_KERNEL_CHECK();
         launched();
-        if (fused0) {  // the ordered records are in the partners now
+        if (fast2) {  // the ordered records are in the partners now
             keys_sorted = std::move(keys_spare_);
             d_sa = std::move(pos_spare_);
         }

@@ -428,8 +428,6 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
     const uint64_t chunks = (n + chunk - 1) / chunk;
     for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
         const uint64_t W0 = c * chunk + (uint64_t)warp * 1024;
-        Fast2Window fw{};
-        if (ks.fast2) fw = fast2_window_load(ks, W0, lane);
         for (int g = 0; g < 32 / kSelectRows; g++) {
             uint64_t k[kSelectRows];
             uint32_t lidx[kSelectRows];
@@ -438,7 +436,7 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
             for (int r = 0; r < kSelectRows; r++) {
                 const int row = g * kSelectRows + r;
                 const uint64_t p = W0 + (uint64_t)row * 32 + lane;
-                uint64_t key = ks.fast2 ? fast2_window_key(ks, fw, W0, row, lane) : (p < n ? key_word(ks, p, 0) : 0ull);
+                uint64_t key = p < n ? key_word(ks, p, 0) : 0ull;
                 bool take = p < n && (!filter || indexed_byte(ks.text[p])) && key >= lo && (hi == 0 || key < hi);
                 k[r] = key;
                 unsigned m = __ballot_sync(0xffffffffu, take);
@@ -468,7 +466,7 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
     }
 }
 
-// Fast-path variant of select_append_kernel.  A warp owns 1024 consecutive positions and lane l the 32 positions
+// Fast-path variant of select_append_kernel (which serves the other alphabets).  A warp owns 1024 consecutive positions and lane l the 32 positions
 // of packed2 word l, so a key is two funnel shifts of registers the lane already holds (no per-row shuffles or
 // ballots).  Phase 1 leaves a 32-bit take mask per lane; phase 2 enumerates the taken positions densely (prefix
 // sums over the lanes, k-th set bit of the owner's mask) so that the records leave the warp as coalesced stores.
@@ -723,234 +721,22 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
     }
 }
 
-// Fast path, after the 4-pass radix sort on the top kFast2SortBits: every group of 2..kFast2SmallGroup keys that
-// tie on the sorted bits is ordered by the full keys.  Tiled: a block stages 1024 records (+ a halo of
-// kFast2SmallGroup) in shared memory with coalesced loads, the thread at the start of each group orders it there
-// (compare-exchange networks for 2..4, rank sort for 5..8), and the tile is written back coalesced.  A group is
-// owned by the tile that holds its first element.  Members of larger groups are marked in the `large` bitmap
-// and left to the refinement.
-constexpr int kGroupTile = 1024;
-__global__ void __launch_bounds__(kBlock) fast2_group_sort_kernel(uint64_t* __restrict__ keys,
-                                                                  uint32_t* __restrict__ pos, uint64_t s,
-                                                                  uint32_t* __restrict__ large) {
-    constexpr int H = kFast2SmallGroup;
-    constexpr int N = kGroupTile + H;  // local index i <-> global t0 + i
-    __shared__ uint64_t sk[N + 1];     // sk[N]: unused pad
-    __shared__ uint32_t sp[N + 1];
-    __shared__ uint32_t first_owned;   // local index of the first element whose group starts in this tile
-    const uint64_t tiles = (s + kGroupTile - 1) / kGroupTile;
-    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * kGroupTile;
-        const uint32_t cnt = (uint32_t)((s - t0) < (uint64_t)N ? (s - t0) : (uint64_t)N);   // staged records
-        const uint32_t own = (uint32_t)((s - t0) < (uint64_t)kGroupTile ? (s - t0) : (uint64_t)kGroupTile);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) {
-            sk[i] = keys[t0 + i];
-            sp[i] = pos[t0 + i];
-        }
-        const uint64_t top_before = t0 ? (keys[t0 - 1] & kFast2TopMask) : 0ull;
-        __syncthreads();
-        if (threadIdx.x == 0) {  // elements that continue the previous tile's last group are not owned
-            uint32_t lead = 0;
-            if (t0) while (lead < own && (sk[lead] & kFast2TopMask) == top_before) lead++;
-            first_owned = lead;
-        }
-        // heads: first element of a run of equal sorted bits
-        for (uint32_t i = threadIdx.x; i < own; i += kBlock) {
-            const uint64_t top = sk[i] & kFast2TopMask;
-            // any window of H + 1 equal elements lies inside a large group: mark it
-            if (i + H < cnt && (sk[i + H] & kFast2TopMask) == top)
-                for (uint64_t t = t0 + i; t <= t0 + i + H; t++) atomicOr(&large[t >> 5], 1u << (t & 31));
-            const bool head = i ? ((sk[i - 1] & kFast2TopMask) != top) : (t0 == 0 || top_before != top);
-            if (!head) continue;
-            uint32_t len = 1;
-            while (len <= (uint32_t)H && i + len < cnt && (sk[i + len] & kFast2TopMask) == top) len++;
-            if (len == 1 || len > (uint32_t)H) continue;
-            if (len <= 4) {
-                uint64_t k0 = sk[i], k1 = sk[i + 1], k2 = len > 2 ? sk[i + 2] : ~0ull, k3 = len > 3 ? sk[i + 3] : ~0ull;
-                if (k0 <= k1 && k1 <= k2 && k2 <= k3) continue;
-                uint32_t p0 = sp[i], p1 = sp[i + 1], p2 = len > 2 ? sp[i + 2] : 0u, p3 = len > 3 ? sp[i + 3] : 0u;
-#define SUFR_CAS(ka, pa, kb, pb)                         \
-    if (kb < ka) {                                       \
-        uint64_t tk = ka; ka = kb; kb = tk;              \
-        uint32_t tp = pa; pa = pb; pb = tp;              \
-    }
-                SUFR_CAS(k0, p0, k1, p1)
-                SUFR_CAS(k2, p2, k3, p3)
-                SUFR_CAS(k0, p0, k2, p2)
-                SUFR_CAS(k1, p1, k3, p3)
-                SUFR_CAS(k1, p1, k2, p2)
-#undef SUFR_CAS
-                sk[i] = k0; sp[i] = p0;
-                sk[i + 1] = k1; sp[i + 1] = p1;
-                if (len > 2) { sk[i + 2] = k2; sp[i + 2] = p2; }
-                if (len > 3) { sk[i + 3] = k3; sp[i + 3] = p3; }
-                continue;
-            }
-            uint64_t k[H];
-            uint32_t p[H];
-#pragma unroll
-            for (int e = 0; e < H; e++) {
-                k[e] = (uint32_t)e < len ? sk[i + e] : ~0ull;
-                p[e] = (uint32_t)e < len ? sp[i + e] : 0u;
-            }
-#pragma unroll
-            for (int e = 0; e < H; e++) {
-                if ((uint32_t)e < len) {
-                    int r = 0;
-#pragma unroll
-                    for (int t = 0; t < H; t++)
-                        if ((uint32_t)t < len && (k[t] < k[e] || (k[t] == k[e] && t < e))) r++;
-                    sk[i + r] = k[e];
-                    sp[i + r] = p[e];
-                }
-            }
-        }
-        __syncthreads();
-        // write back what this tile owns: from its first head up to the end of the last group it started
-        // (that group may reach into the halo; the leading elements of the tile belong to the previous tile)
-        uint32_t last = own;
-        if (first_owned >= own) continue;  // no group starts here (uniform branch: shared value)
-        if (own == (uint32_t)kGroupTile && cnt > own) {
-            const uint64_t top_last = sk[own - 1] & kFast2TopMask;
-            while (last < cnt && (sk[last] & kFast2TopMask) == top_last) last++;
-        }
-        for (uint32_t i = first_owned + threadIdx.x; i < last; i += kBlock) {
-            keys[t0 + i] = sk[i];
-            pos[t0 + i] = sp[i];
-        }
-    }
-}
-
-// Round 0 of the 2-bit fast path, on the array ordered by fast2_group_sort_kernel.  A group is a run of equal
-// canonical keys (fast2_canon): exact ties on all 31 symbols, or the members of a large group.  Everything in
-// a group of size > 1 is collected for the exact refinement (which starts at key word 0).  Boundary LCP =
-// clz(x ^ y) / 2 when neither key contains fill and both neighbours are final (singleton groups), else it is
-// recomputed from the final order (kLcpFixup).  Filtered suffixes (key ~0) sort behind everything.
-__global__ void __launch_bounds__(kBlock) resolve0_fast2_kernel(const uint64_t* __restrict__ keys,
-                                                                const uint32_t* __restrict__ pos, uint64_t s,
-                                                                const uint32_t* __restrict__ large,
-                                                                uint32_t* __restrict__ lcp,
-                                                                uint32_t* __restrict__ act_slot,
-                                                                uint32_t* __restrict__ act_pos,
-                                                                unsigned long long* __restrict__ act_count,
-                                                                uint64_t capacity) {
-    // Four consecutive elements per thread (16-byte loads of keys / positions, one 16-byte LCP store); the
-    // flagged elements of a block iteration (1024 elements) are appended with one global atomic.
-    __shared__ uint32_t wcount[kBlock / 32];
-    __shared__ unsigned long long gbase;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
-    auto is_large = [&](uint64_t i) { return ((large[i >> 5] >> (i & 31)) & 1u) != 0; };
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * 4; base < s; base += stride) {
-        const uint64_t j0 = base + (uint64_t)threadIdx.x * 4;
-        // canonical keys of j0-2 .. j0+4 (index 0 <-> j0-2); raw keys of j0-1 .. j0+3
-        uint64_t c[7], raw[5];
-        uint32_t pp[4] = {0, 0, 0, 0};
-        bool valid[7];
-#pragma unroll
-        for (int t = 0; t < 7; t++) {
-            const long long i = (long long)j0 + t - 2;
-            valid[t] = i >= 0 && (uint64_t)i < s;
-        }
-        if (j0 + 3 < s) {
-            ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + j0);
-            ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(keys + j0 + 2);
-            uint4 p4 = *reinterpret_cast<const uint4*>(pos + j0);
-            raw[1] = a.x; raw[2] = a.y; raw[3] = b2.x; raw[4] = b2.y;
-            pp[0] = p4.x; pp[1] = p4.y; pp[2] = p4.z; pp[3] = p4.w;
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                raw[1 + u] = j0 + u < s ? keys[j0 + u] : 0ull;
-                pp[u] = j0 + u < s ? pos[j0 + u] : 0u;
-            }
-        }
-        raw[0] = valid[1] ? keys[j0 - 1] : 0ull;
-        const uint64_t km2 = valid[0] ? keys[j0 - 2] : 0ull;
-        const uint64_t kp4 = valid[6] ? keys[j0 + 4] : 0ull;
-        c[0] = valid[0] ? fast2_canon(km2, is_large(j0 - 2)) : 0ull;
-#pragma unroll
-        for (int t = 1; t < 6; t++) c[t] = valid[t] ? fast2_canon(raw[t - 1], is_large(j0 + t - 2)) : 0ull;
-        c[6] = valid[6] ? fast2_canon(kp4, is_large(j0 + 4)) : 0ull;
-
-        uint32_t out[4] = {0, 0, 0, 0};
-        uint32_t act = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint64_t j = j0 + u;
-            if (j >= s) break;
-            const int t = u + 2;  // index of element j in c[]
-            const bool next_same = valid[t + 1] && c[t + 1] == c[t];
-            bool head = true;
-            if (j == 0) {
-                out[u] = 0;
-            } else {
-                head = c[t - 1] != c[t];
-                if (!head) {
-                    out[u] = kLcpPending;
-                } else {
-                    const bool prev_multi = valid[t - 2] && j >= 2 && c[t - 2] == c[t - 1];
-                    const uint64_t kp = raw[u], kj = raw[u + 1];
-                    if (((kp | kj) & 1ull) == 0 && !next_same && !prev_multi)
-                        out[u] = (uint32_t)__clzll((long long)(kp ^ kj)) >> 1;
-                    else
-                        out[u] = kLcpFixup;
-                }
-            }
-            if (!head || next_same) act |= 1u << u;
-        }
-        if (j0 + 3 < s) {
-            *reinterpret_cast<uint4*>(lcp + j0) = make_uint4(out[0], out[1], out[2], out[3]);
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (j0 + u < s) lcp[j0 + u] = out[u];
-        }
-        // append: per-thread count -> warp prefix -> block prefix -> one atomic
-        const uint32_t mine = __popc(act);
-        uint32_t incl = mine;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += o;
-        }
-        if (lane == 31) wcount[warp] = incl;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t acc = 0;
-            for (int w = 0; w < kBlock / 32; w++) {
-                uint32_t tt = wcount[w];
-                wcount[w] = acc;
-                acc += tt;
-            }
-            gbase = acc ? atomicAdd(act_count, (unsigned long long)acc) : 0ull;
-        }
-        __syncthreads();
-        unsigned long long idx = gbase + wcount[warp] + incl - mine;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (act & (1u << u)) {
-                if (idx < capacity) {
-                    act_slot[idx] = (uint32_t)(j0 + u);
-                    act_pos[idx] = pp[u];
-                }
-                idx++;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Group ordering and round 0 of the fast path in ONE pass over the radix-sorted records (the two kernels above,
-// fused; same results).  Per tile of 1024 records (+ 9 before, + 8 behind) staged in shared memory:
+// Fast path, after the 4-pass radix sort on the top kFast2SortBits: group ordering and round 0 in ONE pass over the
+// radix-sorted records.  A run is a maximal sequence of records that tie on the sorted bits.  Runs of 2..8 are
+// ordered by their full 31-symbol keys; members of longer runs are marked in the `large` bitmap and left to the
+// refinement.  A group is then a run of equal canonical keys (fast2_canon): exact ties on all 31 symbols, or
+// the members of a large run; everything in a group of size > 1 is collected for the exact refinement (which
+// starts at key word 0).  Boundary LCP = clz(x ^ y) / 2 when neither key contains fill and both neighbours are
+// final (singleton groups), else it is recomputed from the final order (kLcpFixup).  Filtered suffixes (key ~0)
+// sort behind everything.
+// Per tile of 1024 records (+ 9 before, + 8 behind) staged in shared memory:
 //   phase 0: bitmap of run heads (record whose sorted bits differ from its predecessor's); from it every record
 //            gets the extent of its run with two shifts and a clz / ffs.  A run of >= 9 records is "large";
 //   phase 1: records of runs of 2..8 compute their rank inside the run by counting (every thread does the same
 //            bounded work, no per-group serial sorting) -> the tile in final order in a second buffer;
 //   phase 2: per record this tile owns (its run's head lies in the tile, or the run is large and the record itself
-//            does): boundary LCP / pending / fix-up and the unresolved flag exactly as resolve0_fast2_kernel;
-//            unresolved records are appended with one global atomic per tile.
+//            does): boundary LCP / pending / fix-up mark and the unresolved flag; unresolved records are appended
+//            with one global atomic per tile.
 // Runs that are cut off by the staging window are either long enough to be known large or are not adjacent to
 // anything this tile emits.  OUT OF PLACE (the radix sort's ping-pong partners receive the ordered records): a tile
 // reads records that a neighbouring tile orders, so an in-place update would race.

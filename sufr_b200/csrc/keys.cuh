@@ -48,7 +48,7 @@ struct KeySpec {
 // Fast-path keys: bit 0 = the key contains fill (an irregular symbol inside its 31-symbol window),
 // bits 63..2 = 31 symbols.  The radix sort covers only the top kFast2SortBits (4 passes); groups of up to
 // kFast2SmallGroup keys that tie on those bits are then ordered by their full keys in registers
-// (fast2_group_sort_kernel), larger groups and exact ties on all 31 symbols go to the 3-bit refinement.
+// (round0_fast2_kernel), larger groups and exact ties on all 31 symbols go to the 3-bit refinement.
 constexpr int kShardHistBits = 12;   // multi-GPU key ranges are cut at multiples of 2^(64 - kShardHistBits)
 constexpr int kFast2Symbols = 31;
 constexpr int kFast2SortBits = 32;
@@ -148,39 +148,6 @@ __device__ __forceinline__ uint64_t first_key_fast2(const KeySpec& ks, uint64_t 
 __device__ __forceinline__ uint64_t first_key(const KeySpec& ks, uint64_t p);
 // out-of-line copy for the rare irregular windows inside unrolled loops
 __device__ __noinline__ uint64_t first_key_fast2_slow(const KeySpec& ks, uint64_t p) { return first_key_fast2(ks, p); }
-
-// Warp-cooperative key generation on the fast path: a warp owns 1024 consecutive positions starting at W0
-// (a multiple of 1024).  Lane l holds packed2 word W0/32 + l and (l <= 16) irr word W0/64 + l; the key of
-// position W0 + 32 r + lane is assembled from two shuffled words instead of four global loads.
-struct Fast2Window {
-    uint64_t w, w_ext, ir;
-};
-__device__ __forceinline__ Fast2Window fast2_window_load(const KeySpec& ks, uint64_t W0, int lane) {
-    Fast2Window fw;
-    uint64_t q = (W0 >> 5) + lane;
-    fw.w = q < ks.packed2_words ? __ldg(ks.packed2 + q) : 0ull;
-    uint64_t qe = (W0 >> 5) + 32;
-    fw.w_ext = qe < ks.packed2_words ? __ldg(ks.packed2 + qe) : 0ull;
-    uint64_t qi = (W0 >> 6) + lane;
-    fw.ir = (lane <= 16 && qi < ks.irr_words) ? __ldg(ks.irr + qi) : ~0ull;
-    return fw;
-}
-// r is warp-uniform
-__device__ __forceinline__ uint64_t fast2_window_key(const KeySpec& ks, const Fast2Window& fw, uint64_t W0, int r,
-                                                     int lane) {
-    uint64_t hi = __shfl_sync(0xffffffffu, fw.w, r);
-    uint64_t lo = __shfl_sync(0xffffffffu, fw.w, (r + 1) & 31);
-    if (r == 31) lo = fw.w_ext;
-    uint64_t w = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-    uint64_t i0 = __shfl_sync(0xffffffffu, fw.ir, r >> 1);
-    uint64_t i1 = __shfl_sync(0xffffffffu, fw.ir, (r >> 1) + 1);
-    uint32_t bit = (uint32_t)(r & 1) * 32u + (uint32_t)lane;
-    uint64_t m = bit ? ((i0 << bit) | (i1 >> (64 - bit))) : i0;
-    m &= ~0ull << (64 - kFast2Symbols);
-    w &= ~3ull;
-    if (m == 0) return w;
-    return first_key_fast2(ks, W0 + (uint64_t)r * 32 + lane);  // window contains an irregular symbol (rare)
-}
 
 // Number of symbols that exist in the key of suffix p.
 __device__ __forceinline__ uint64_t key_len(const KeySpec& ks, uint64_t p) {
