@@ -145,7 +145,8 @@ int sufr_b200_write(const SufrB200Args* args, const SufrB200Result* result);
  *    what the reference's builder struct holds after `new` (sufr_builder.rs:38-89): counts, the
  *    transformed text, n_ranges -- `sa` and `lcp` are NULL, they are in the file.  timings.d2h_ms is
  *    the wall time of that streaming write.  Free with sufr_b200_result_free(NULL, out).
- *    `out` may be NULL. */
+ *    `out` may be NULL.  Single process only (world_size <= 1): sharded builds go through
+ *    sufr_b200_build / sufr_b200_patch_seam / sufr_b200_write. */
 int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out);
 
 /* -- helpers shared with the host-side mirror ---------------------------------------------- */

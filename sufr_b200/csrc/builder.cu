@@ -599,12 +599,8 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         if (n) {
             if (ks.fast2 && !descending) {
                 // one block per block of the sort's first pass, which then needs no histogram pass of its own
-                static bool attr_set = false;
-                if (!attr_set) {
-                    SUFR_CUDA_CHECK(cudaFuncSetAttribute(keygen_fast2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         kKeygenSmem));
-                    attr_set = true;
-                }
+                static bool attr_set[64] = {};
+                allow_dynamic_smem(keygen_fast2_kernel, kKeygenSmem, attr_set);
                 const rsort::Plan plan = rsort::make_plan<uint64_t, uint32_t>(n);
                 const uint64_t chunk = (uint64_t)plan.tiles_per_block * rsort::BLOCK * rsort::Tuning<uint64_t, uint32_t>::IPT;
                 d_counts = dalloc<uint32_t>(rsort::counts_words());
@@ -1721,6 +1717,10 @@ int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out) 
     SufrB200Result* res = out ? out : &local;
     int rc = guarded([&] {
         if (!args) throw Error(SUFR_B200_ERR_ARGUMENT, "args is NULL");
+        if (args->world_size > 1)
+            throw Error(SUFR_B200_ERR_ARGUMENT,
+                        "sufr_b200_create is the single-process path; a sharded build exchanges (count, first, last) "
+                        "between sufr_b200_build and sufr_b200_write");
         std::unique_ptr<Ctx> ctx(make_ctx(device));
         SufrB200Result dev;
         memset(&dev, 0, sizeof(dev));

@@ -27,6 +27,17 @@ struct Error : std::runtime_error {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per device (the attribute is per device).
+template <typename Kernel>
+inline void allow_dynamic_smem(Kernel kernel, size_t bytes, bool (&done)[64]) {
+    int dev = 0;
+    SUFR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        SUFR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+}
+
 inline uint32_t div_up_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 

@@ -290,12 +290,8 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
     if (n == 0 || end_bit <= begin_bit) return false;
     Plan p = make_plan<K, V>(n);
     constexpr size_t ex_bytes = 2 * (sizeof(K) + sizeof(V)) * BLOCK * IPT;  // exchange + prefetch buffers
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        SUFR_CUDA_CHECK(cudaFuncSetAttribute(downsweep_kernel<K, V, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ex_bytes));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};  // per instantiation and device
+    allow_dynamic_smem(downsweep_kernel<K, V, IPT>, ex_bytes, attr_set);
     bool in_b = false;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
         int nb = end_bit - bit < RADIX_BITS ? end_bit - bit : RADIX_BITS;

@@ -167,6 +167,17 @@ def test_parallel_fasta_ingest_matches_serial_restatement(S, tmp_path, seed, rec
     assert a.seq == b.seq
 
 
+def test_create_rejects_sharded_arguments(S):
+    from sufr_b200 import _lib
+    import ctypes as C
+    args = _lib.Args()
+    args.world_size = 2
+    args.rank = 1
+    rc = _lib.lib().sufr_b200_create(C.byref(args), 0, None)
+    assert rc == _lib.ERR_ARGUMENT
+    assert b"single-process" in _lib.lib().sufr_b200_last_error()
+
+
 def _host_result(S, o, shard=None):
     """A SufrB200Result in host memory filled from oracle arrays (exercises the writer without a GPU)."""
     from sufr_b200 import _lib
