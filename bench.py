@@ -71,15 +71,44 @@ def synth_prefix_numpy(n: int, text_len: int, starts, seed: int = SEED) -> bytes
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """Samples SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md): through NVML every
+    10 ms when pynvml is importable (a multi-GPU timed region lasts ~150 ms), else through nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]  # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
-    def __init__(self, index: int):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+    def __init__(self, index: int, uuid: str = None):
+        self.index, self.uuid = index, uuid
+        self.samples, self._stop, self._t = [], threading.Event(), None  # [sm, sm_max, watts, 4 x "Active"/"Not Active"]
+        self.source = "nvidia-smi"
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def _run(self):
+        try:
+            nv, h = self._nvml_handle()
+            sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.source = "nvml"
+            while not self._stop.is_set():
+                mask = reasons_fn(h)
+                self.samples.append([nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), sm_max, nv.nvmlDeviceGetPowerUsage(h) / 1000.0]
+                                    + ["Active" if mask & b else "Not Active" for b in self.BITS])
+                self._stop.wait(0.01)
+            return
+        except Exception:
+            if self.samples:
+                return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -104,10 +133,9 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        reasons = [nm for k, nm in enumerate(self.NAMES) if any(str(s[3 + k]).lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples), "source": self.source}
 
 
 def oracle_run(sample: bytes, threads: int, partitions: int):
@@ -223,7 +251,11 @@ def main():
         step_device().free()
     barrier()
     results = []
-    with ClockSampler(local_rank) as clocks:
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local_rank, gpu_uuid) as clocks:
         t0 = time.perf_counter()
         for _ in range(args.steps):
             r = step_device()
