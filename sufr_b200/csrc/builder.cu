@@ -249,6 +249,8 @@ class Build {
         wide_slots_.reset();
         wide_m_ = 0;
     }
+    uint64_t sort_kmask_ = ~0ull;  // general path: key bits covered by the first sort (see make_keys_and_sort)
+    bool partial_sort_ = false;
     DevBuf<uint64_t> keys_spare_;  // fast path: the radix sort's ping-pong partners, output of the fused round 0
     DevBuf<uint32_t> pos_spare_;
     DevBuf<uint32_t> d_isa;     // inverse suffix array (only when prefix doubling ran)
@@ -550,7 +552,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     if (prefilter && n) kept = indexed_count_;
     // Few filtered suffixes (the common case: delimiters, sparse N): no compaction at all, they get the
     // key ~0 and drop off the end of the sorted array.  Needs an unused low bit in the packed word.
-    const bool sentinel = prefilter && !sharded && used_bits < 64 && (n - kept) * 16 <= n;
+    const bool sentinel = prefilter && !sharded && used_bits < 64 && kept < n && (n - kept) * 16 <= n;
     sentinel_ = sentinel;
     if (sharded && ks.mode == kModeFull) {
         // unordered selection: one key computation per position, capacity from the sampled histogram
@@ -620,7 +622,20 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     if (!first_counts_ready) d_counts = dalloc<uint32_t>(rsort::counts_words());
     // 3-bit keys: all used bits (sentinel keys have the unused low bits set, so those join the sort then).
     // 2-bit fast path: only the top kFast2SortBits; ties go to the exact refinement.
-    const int begin_bit = ks.fast2 ? 64 - kFast2SortBits : (sentinel ? 0 : 64 - used_bits);
+    // General path: about log2(n) + 8 bits (rounded up to whole passes) separate all but ~1/256 of the
+    // neighbours; the elements that still agree on them are refined from key word 0 like any other tie.
+    // (Not with sentinel keys: their order relies on the low bits.)
+    int begin_bit = ks.fast2 ? 64 - kFast2SortBits : (sentinel ? 0 : 64 - used_bits);
+    partial_sort_ = false;
+    sort_kmask_ = ~0ull;
+    if (!ks.fast2 && !sentinel && !getenv("SUFR_B200_DEBUG_FULL_WORD_SORT")) {
+        const int want = ((bits_for(sort_n ? sort_n - 1 : 0) + 8 + rsort::RADIX_BITS - 1) / rsort::RADIX_BITS) * rsort::RADIX_BITS;
+        if (want < used_bits) {
+            begin_bit = 64 - want;
+            partial_sort_ = true;
+            sort_kmask_ = ~0ull << begin_bit;
+        }
+    }
     bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), sort_n,
                                                       begin_bit, 64, d_counts.get(), st(), &ctx.launches,
                                                       &downsweep_events, first_counts_ready);
@@ -663,7 +678,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // round 0: boundaries of the initial sort, fused with the collection of the unresolved elements.
     // `word` is the last key word (3-bit packing) the groups are known to agree on; the fast path has only
     // sorted a 2-bit approximation of the first symbols, so its refinement starts with word 0.
-    int word = fast2 ? -1 : 0;
+    int word = (fast2 || partial_sort_) ? -1 : 0;
     int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
     DevBuf<uint32_t> large;  // fast path: members of large groups that the register sort left alone
     if (fast2) {
@@ -672,7 +687,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     }
     // the fast path's round 0 is out of place: the ordered records land in the sort's ping-pong partners
     ViewAll v0{fast2 ? keys_spare_.get() : keys_sorted.get(), fast2 ? pos_spare_.get() : d_sa.get(),
-               fast2 ? large.get() : nullptr};
+               fast2 ? large.get() : nullptr, fast2 ? ~0ull : sort_kmask_};
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, pos, seg;
     {
@@ -702,7 +717,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                                                                       wide_sa_.get(), wide_lcp_.get());
         } else {
             resolve0_append_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks, final_word,
-                                                                         d_lcp.get(), act_slot.get(), act_pos.get(),
+                                                                         sort_kmask_, d_lcp.get(), act_slot.get(), act_pos.get(),
                                                                          d_cnt.get(), capacity);
         }
         SUFR_KERNEL_CHECK();

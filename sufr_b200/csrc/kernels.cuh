@@ -605,8 +605,9 @@ struct ViewAll {
     const uint64_t* key;
     const uint32_t* pos;
     const uint32_t* large;  // fast path: bitmap of the members of large, only partially sorted groups (else NULL)
+    uint64_t kmask;         // general path: the key bits the first sort covered (a group = equal on those bits)
     __device__ uint64_t k(uint64_t i) const {
-        return large ? fast2_canon(key[i], (large[i >> 5] >> (i & 31)) & 1u) : key[i];
+        return large ? fast2_canon(key[i], (large[i >> 5] >> (i & 31)) & 1u) : (key[i] & kmask);
     }
     __device__ uint64_t raw(uint64_t i) const { return key[i]; }
     __device__ uint32_t p(uint64_t i) const { return pos[i]; }
@@ -682,9 +683,11 @@ __device__ __forceinline__ void block_append(bool active, uint32_t slot_val, uin
 // Round 0 in one pass over the sorted keys: LCP of every boundary (as resolve_kernel) and, because the
 // unresolved elements are normally a tiny fraction, an UNORDERED warp-aggregated append of (slot, position)
 // of every element that is still in a group of size > 1.  The short list is then sorted by slot.
+// `kmask` = the key bits the first sort covered: when it stopped short of the whole word (Build::sort_bits),
+// elements that agree on those bits form the groups, and the refinement starts over with key word 0.
 __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t* __restrict__ keys,
                                                                  const uint32_t* __restrict__ pos, uint64_t s,
-                                                                 KeySpec ks, int final_word,
+                                                                 KeySpec ks, int final_word, uint64_t kmask,
                                                                  uint32_t* __restrict__ lcp,
                                                                  uint32_t* __restrict__ act_slot,
                                                                  uint32_t* __restrict__ act_pos,
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
                 lcp[0] = 0;
             } else {
                 uint64_t kp = keys[j - 1];
-                head = kp != kj;
+                head = ((kp ^ kj) & kmask) != 0;  // they differ inside the sorted bits: clz(kp ^ kj) is exact
                 if (head) {
                     lcp[j] = lcp_from_words(ks, kp, kj, 0, pos[j - 1], p);
                 } else if (final_word) {
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
                     lcp[j] = kLcpPending;
                 }
             }
-            if (!final_word) active = !head || (j + 1 < s && keys[j + 1] == kj);
+            if (!final_word) active = !head || (j + 1 < s && ((keys[j + 1] ^ kj) & kmask) == 0);
         }
         block_append(active, (uint32_t)j, p, act_slot, act_pos, act_count, capacity, wcount, &gbase);
     }
