@@ -583,7 +583,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             capacity = c;
         }
         sort_n = s;
-    } else if (sharded || (prefilter && !sentinel)) {
+    } else if (sharded || (prefilter && !sentinel && kept < n)) {
         SelectIn in{ks, n, descending, sharded ? 1 : 0, lo, hi, d_text.get(), prefilter ? 1 : 0};
         s = sharded ? shard_count : kept;  // both exact: histogram of indexed suffixes / indexed count
         keys_a = dalloc<uint64_t>(s);
@@ -625,12 +625,15 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     // General path: about log2(n) + 8 bits (rounded up to whole passes) separate all but ~1/256 of the
     // neighbours; the elements that still agree on them are refined from key word 0 like any other tie.
     // (Not with sentinel keys: their order relies on the low bits.)
-    int begin_bit = ks.fast2 ? 64 - kFast2SortBits : (sentinel ? 0 : 64 - used_bits);
+    // A capped key (seed mask of weight W, --max-query-len Q) has only cap * bits meaningful bits; the rest is 0.
+    int key_bits = used_bits;
+    if (ks.mode != kModeFull && ks.cap < (uint64_t)ks.pt.K) key_bits = (int)ks.cap * (int)ks.pt.bits;
+    int begin_bit = ks.fast2 ? 64 - kFast2SortBits : (sentinel ? 0 : 64 - key_bits);
     partial_sort_ = false;
     sort_kmask_ = ~0ull;
     if (!ks.fast2 && !sentinel && !getenv("SUFR_B200_DEBUG_FULL_WORD_SORT")) {
         const int want = ((bits_for(sort_n ? sort_n - 1 : 0) + 8 + rsort::RADIX_BITS - 1) / rsort::RADIX_BITS) * rsort::RADIX_BITS;
-        if (want < used_bits) {
+        if (want < key_bits) {
             begin_bit = 64 - want;
             partial_sort_ = true;
             sort_kmask_ = ~0ull << begin_bit;
