@@ -389,9 +389,11 @@ def verify_sample(res, d_text, k, rank, world):
     g = torch.Generator(device="cpu")
     g.manual_seed(1234 + rank)
     j = torch.randint(1, s, (k,), generator=g).to(sa.device)
-    a = sa[j - 1].cpu().numpy().astype(np.int64)
-    b = sa[j].cpu().numpy().astype(np.int64)
-    l = lcp[j].cpu().numpy().astype(np.int64)
+    # u32 results are viewed as int32 tensors: positions >= 2^31 come out negative, mask them back
+    wrap = 0xFFFFFFFF if sa.dtype == torch.int32 else 0x7FFFFFFFFFFFFFFF
+    a = sa[j - 1].cpu().numpy().astype(np.int64) & wrap
+    b = sa[j].cpu().numpy().astype(np.int64) & wrap
+    l = lcp[j].cpu().numpy().astype(np.int64) & wrap
     n = d_text.numel()
     W = 256
     bad = 0
@@ -409,6 +411,8 @@ def verify_sample(res, d_text, k, rank, world):
     out = {"pairs": k, "mismatches": bad}
     if world == 1:
         tot = int(sa.sum(dtype=torch.int64).item())
+        if sa.dtype == torch.int32:
+            tot += int((sa < 0).sum().item()) << 32
         # all positions except the delimiters ('%' is not indexed under --dna)
         expect = n * (n - 1) // 2 - int(torch.nonzero(d_text == ord("%")).sum().item())
         out["position_sum_ok"] = (tot == expect)

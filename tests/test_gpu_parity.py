@@ -285,6 +285,34 @@ def test_bench_workload_generator_matches_cpu_restatement(S):
     assert got.count(b"%") == 23 and got.endswith(b"$")
 
 
+@pytest.mark.parametrize("bits", [32, 64])
+def test_positions_above_2_31(S, bits):
+    """2.3 Gbp: suffix positions that do not fit 31 bits, u32 and u64 results (what `sufr create` writes for a
+    human genome is u32).  Checked with the size-independent sample check of the bench."""
+    import torch
+    import bench
+    from sufr_b200 import _lib
+    if torch.cuda.get_device_properties(0).total_memory < 120 * 2**30:
+        pytest.skip("needs ~100 GB of device memory")
+    text_len, starts = bench.record_layout(2_300_000_000)
+    ctx = S.default_context(0)
+    d = torch.empty(text_len, dtype=torch.uint8, device="cuda")
+    st = np.asarray(starts, dtype=np.uint64)
+    assert _lib.lib().sufr_b200_synth_dna(ctx.handle, d.data_ptr(), text_len, bench.SEED, st.ctypes.data, len(st),
+                                          ord("%")) == 0
+    r = S.build(S.SufrBuilderArgs(text=b"", is_dna=True), index_bits=bits, ctx=ctx, result_memory=S.MEM_DEVICE,
+                device_text=(d.data_ptr(), text_len))
+    try:
+        assert r.num_suffixes == text_len - 23
+        v = bench.verify_sample(r, d, 1500, 0, 1)
+        assert v["mismatches"] == 0 and v["position_sum_ok"], v
+    finally:
+        r.free()
+        del d
+        ctx.trim()
+        torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("n", [10_000_000])
 def test_config1_10mbp_random_dna(S, n):
     """BASELINE configs[0]: `sufr create --dna -n 16` on 10 Mbp random ACGT, u32 -- bit-exact vs the oracle."""
