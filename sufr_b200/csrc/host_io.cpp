@@ -120,6 +120,26 @@ SufrFrame make_sufr_frame(const SufrB200Args& args, uint32_t index_bits, uint64_
     return f;
 }
 
+// A section of tens of GB written by several threads (page-cache copies are CPU bound; disks like a deep queue).
+static void pwrite_parallel(int fd, const void* buf, size_t len, uint64_t off, const std::string& path) {
+    size_t piece = 256u << 20;
+    if (const char* dbg = getenv("SUFR_B200_DEBUG_WRITE_PIECE")) piece = std::max<size_t>(1, strtoull(dbg, nullptr, 10));
+    size_t T = std::thread::hardware_concurrency();
+    T = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(T, 8), len / piece));
+    if (T <= 1) { pwrite_all(fd, buf, len, off, path); return; }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(T);
+    for (size_t t = 0; t < T; t++)
+        pool.emplace_back([&, t]() {
+            try {
+                const size_t lo = len * t / T, hi = len * (t + 1) / T;
+                pwrite_all(fd, (const char*)buf + lo, hi - lo, off + lo, path);
+            } catch (...) { err[t] = std::current_exception(); }
+        });
+    for (auto& th : pool) th.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+}
+
 void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
     const std::string path = args.path ? args.path : "out.sufr";  // sufr_builder.rs:215
     const size_t w = r.index_bits / 8;
@@ -135,13 +155,13 @@ void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
     try {
         if (leader) {
             pwrite_all(fd, head.data(), head.size(), 0, path);
-            pwrite_all(fd, r.text, r.text_len, text_pos, path);
+            pwrite_parallel(fd, r.text, r.text_len, text_pos, path);
             pwrite_all(fd, tail.data(), tail.size(), names_pos, path);
             if (sharded && ftruncate(fd, (off_t)(names_pos + tail.size())) != 0)
                 throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
         }
-        pwrite_all(fd, r.sa, r.num_suffixes * w, sa_pos + r.shard_offset * w, path);
-        pwrite_all(fd, r.lcp, r.num_suffixes * w, lcp_pos + r.shard_offset * w, path);
+        pwrite_parallel(fd, r.sa, r.num_suffixes * w, sa_pos + r.shard_offset * w, path);
+        pwrite_parallel(fd, r.lcp, r.num_suffixes * w, lcp_pos + r.shard_offset * w, path);
     } catch (...) {
         close(fd);
         throw;

@@ -216,6 +216,21 @@ def test_sufr_writer_matches_golden_bytes(S, tmp_path, golden, fasta, flags, wor
     assert out.read_bytes() == (GOLDEN / "expected" / golden).read_bytes()
 
 
+def test_writer_sections_written_by_several_threads(S, tmp_path, monkeypatch):
+    """Large sections are cut into pieces that several threads pwrite; forced on a small file here."""
+    from sufr_b200 import _lib
+    from sufr_b200.builder import _CArgs
+    monkeypatch.setenv("SUFR_B200_DEBUG_WRITE_PIECE", "1000")
+    seq = S.read_sequence_file(GOLDEN / "inputs" / "uniprot.fa", b"%")
+    o = O.oracle_build(seq.seq, sequence_starts=seq.start_positions, sequence_names=seq.sequence_names)
+    out = tmp_path / "out.sufr"
+    args = S.SufrBuilderArgs(text=seq.seq, path=str(out), sequence_starts=seq.start_positions,
+                             sequence_names=seq.sequence_names)
+    r, keep = _host_result(S, o)
+    assert _lib.lib().sufr_b200_write(C.byref(_CArgs(args).c), C.byref(r)) == 0
+    assert out.read_bytes() == (GOLDEN / "expected" / "uniprot.sufr").read_bytes()
+
+
 def test_writer_u64_layout(S, tmp_path):
     from sufr_b200 import _lib
     from sufr_b200.builder import _CArgs
