@@ -227,7 +227,8 @@ def test_writer_sections_written_by_several_threads(S, tmp_path, monkeypatch):
     args = S.SufrBuilderArgs(text=seq.seq, path=str(out), sequence_starts=seq.start_positions,
                              sequence_names=seq.sequence_names)
     r, keep = _host_result(S, o)
-    assert _lib.lib().sufr_b200_write(C.byref(_CArgs(args).c), C.byref(r)) == 0
+    c = _CArgs(args)
+    assert _lib.lib().sufr_b200_write(C.byref(c.c), C.byref(r)) == 0
     assert out.read_bytes() == (GOLDEN / "expected" / "uniprot.sufr").read_bytes()
 
 
