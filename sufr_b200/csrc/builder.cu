@@ -683,7 +683,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // sorted a 2-bit approximation of the first symbols, so its refinement starts with word 0.
     int word = (fast2 || partial_sort_) ? -1 : 0;
     int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
-    DevBuf<uint32_t> large;  // fast path: members of large groups that the register sort left alone
+    DevBuf<uint32_t> large;  // fast path: members of runs too long to be ordered inside round 0 (kernels.cuh)
     if (fast2) {
         large = dalloc<uint32_t>(r0n / 32 + 1);
         SUFR_CUDA_CHECK(cudaMemsetAsync(large.get(), 0, (r0n / 32 + 1) * 4, st()));

@@ -466,9 +466,9 @@ __global__ void __launch_bounds__(kBlock) select_append_kernel(KeySpec ks, uint6
     }
 }
 
-// Fast-path variant of select_append_kernel (which serves the other alphabets).  A warp owns 1024 consecutive positions and lane l the 32 positions
-// of packed2 word l, so a key is two funnel shifts of registers the lane already holds (no per-row shuffles or
-// ballots).  Phase 1 leaves a 32-bit take mask per lane; phase 2 enumerates the taken positions densely (prefix
+// Fast-path variant of select_append_kernel (which serves the other alphabets).  A warp owns 1024 consecutive
+// positions and lane l the 32 positions of packed2 word l, so a key is two funnel shifts of registers the lane
+// already holds (no per-row shuffles or ballots).  Phase 1 leaves a 32-bit take mask per lane; phase 2 enumerates the taken positions densely (prefix
 // sums over the lanes, k-th set bit of the owner's mask) so that the records leave the warp as coalesced stores.
 __device__ __forceinline__ uint32_t select_bit(uint32_t m, uint32_t k) {  // position of the k-th (0-based) set bit
     uint32_t pos = 0, c;

@@ -40,7 +40,7 @@ struct KeySpec {
     const uint64_t* irr;       // 1 bit per symbol, 64 per word: symbol is not one of the 4 regular bytes (or is beyond the text)
     const uint8_t* text;       // transformed text
     const uint8_t* cls;        // [256] byte -> number of regular bytes smaller than it (0..4); regular bytes: their rank
-    uint64_t packed2_words;    // allocation sizes (bounds of the warp-window loads)
+    uint64_t packed2_words;    // allocation sizes (bounds of the per-lane word loads)
     uint64_t irr_words;
     int reg_indexed;           // every regular byte is one of ACGT$: only irregular positions can be filtered out
 };
