@@ -546,7 +546,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     DevBuf<uint64_t> keys_a, keys_b;
     DevBuf<uint32_t> pos_a, pos_b;
     const int used_bits = (int)(ks.pt.K * ks.pt.bits);
-    bool first_counts_ready = false;
+    bool first_digit_done = false;  // fast path: the records come out of key generation sorted by the first digit
     uint64_t kept = n;     // suffixes that survive the filter (all ranks' ranges together)
     uint64_t sort_n = n;   // elements handed to the sort
     if (prefilter && n) kept = indexed_count_;
@@ -600,15 +600,25 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         pos_a = dalloc<uint32_t>(n);
         if (n) {
             if (ks.fast2 && !descending) {
-                // one block per block of the sort's first pass, which then needs no histogram pass of its own
+                // key generation fused with the first radix pass (kernels.cuh): histogram of the first digit per
+                // block, scan, then generate + scatter; the sort proper starts at the second digit
                 static bool attr_set[64] = {};
-                allow_dynamic_smem(keygen_fast2_kernel, kKeygenSmem, attr_set);
-                const rsort::Plan plan = rsort::make_plan<uint64_t, uint32_t>(n);
-                const uint64_t chunk = (uint64_t)plan.tiles_per_block * rsort::BLOCK * rsort::Tuning<uint64_t, uint32_t>::IPT;
+                allow_dynamic_smem(fast2_keygen_scatter_kernel, kKsSmem, attr_set);
+                const uint64_t tiles = div_up(n, kKsTile);
+                const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)kNumSMs * 4);
+                const uint64_t chunk = div_up(tiles, grid) * kKsTile;
+                const uint32_t used_grid = (uint32_t)div_up(n, chunk);
+                const int shift = 64 - kFast2SortBits;
                 d_counts = dalloc<uint32_t>(rsort::counts_words());
-                keygen_fast2_kernel<<<plan.grid, kBlock, kKeygenSmem, st()>>>(ks, n, sentinel ? 1 : 0, keys_a.get(), pos_a.get(),
-                                                                             chunk, 64 - kFast2SortBits, d_counts.get());
-                first_counts_ready = true;
+                fast2_first_digit_hist_kernel<<<used_grid, kBlock, 0, st()>>>(ks, n, sentinel ? 1 : 0, chunk, shift,
+                                                                             d_counts.get());
+                SUFR_KERNEL_CHECK();
+                rsort::scan_counts_kernel<<<1, 1024, 0, st()>>>(d_counts.get(), (uint32_t)rsort::RADIX * used_grid);
+                SUFR_KERNEL_CHECK();
+                fast2_keygen_scatter_kernel<<<used_grid, kBlock, kKsSmem, st()>>>(ks, n, sentinel ? 1 : 0, keys_a.get(),
+                                                                                pos_a.get(), chunk, shift, d_counts.get());
+                launched(2);
+                first_digit_done = true;
             } else
                 keygen_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(ks, n, descending, d_text.get(), sentinel ? 1 : 0,
                                                                   keys_a.get(), pos_a.get());
@@ -619,7 +629,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     t_keys_mark = timer.mark();
     keys_b = dalloc<uint64_t>(sort_n);
     pos_b = dalloc<uint32_t>(sort_n);
-    if (!first_counts_ready) d_counts = dalloc<uint32_t>(rsort::counts_words());
+    if (!first_digit_done) d_counts = dalloc<uint32_t>(rsort::counts_words());
     // 3-bit keys: all used bits (sentinel keys have the unused low bits set, so those join the sort then).
     // 2-bit fast path: only the top kFast2SortBits; ties go to the exact refinement.
     // General path: about log2(n) + 8 bits (rounded up to whole passes) separate all but ~1/256 of the
@@ -640,8 +650,8 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
         }
     }
     bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(keys_a.get(), keys_b.get(), pos_a.get(), pos_b.get(), sort_n,
-                                                      begin_bit, 64, d_counts.get(), st(), &ctx.launches,
-                                                      &downsweep_events, first_counts_ready);
+                                                      begin_bit + (first_digit_done ? rsort::RADIX_BITS : 0), 64, d_counts.get(),
+                                                      st(), &ctx.launches, &downsweep_events);
     sorted_elements = sort_n;
     sort_n_ = sort_n;
     if (in_b) {

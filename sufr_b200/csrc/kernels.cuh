@@ -255,66 +255,78 @@ __global__ void __launch_bounds__(kBlock) keygen_kernel(KeySpec ks, uint64_t n, 
     }
 }
 
-// Fast-path variant of keygen_kernel, ascending order.  A warp owns 1024 consecutive positions and lane l the 32
-// positions of packed2 word l, so a key is two funnel shifts of registers the lane already holds; the 32 x 32 keys
-// are transposed through shared memory (in two halves of 16 keys per lane, which keeps four blocks of the sort's
-// 4-per-SM grid resident) so that the stores are coalesced.  Block b generates exactly the records
-// of block b of the radix sort's first pass (`chunk_elems` = tiles_per_block x tile) and leaves that pass's digit
-// histogram in `counts` ([digit][block], what rsort::upsweep_kernel would compute from the keys).
-constexpr int kKeygenSmem = (kBlock / 32) * 32 * 17 * 8;
-__global__ void __launch_bounds__(kBlock) keygen_fast2_kernel(KeySpec ks, uint64_t n, int filter,
-                                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ pos,
-                                                              uint64_t chunk_elems, int hist_shift,
-                                                              uint32_t* __restrict__ counts) {
+// Fast path, unsharded: key generation FUSED with the first radix pass.  The first pass of an LSD sort need not be
+// stable (there is no earlier order to preserve; the full sort has no true ties, so the order among records that
+// agree on the sorted bits never reaches the result), so its ranking is one shared-memory atomic per record
+// instead of eight ballots, and the 37 GB of records are written once, already in first-digit order, instead of
+// written in text order and read back.  A warp owns 1024 consecutive positions and lane l the 32 positions of
+// packed2 word l, so a key is two funnel shifts of registers the lane already holds.
+//   fast2_first_digit_hist_kernel: [digit][block] histogram of the first digit (block b = the positions of block b
+//                                  of the scatter kernel), scanned by rsort::scan_counts_kernel;
+//   fast2_keygen_scatter_kernel:   per tile of 8192 positions: rank of every record inside its (tile, digit) by
+//                                  atomicAdd, digit starts by a 256-wide scan, records placed in shared memory at
+//                                  start + rank, coalesced copy to the digit's cursor in the output.
+struct Fast2Lane {  // what a lane needs to form the 32 keys of its packed2 word
+    uint64_t w, wn, M, P0;
+};
+struct Fast2LaneRaw {  // the global loads of fast2_lane_load, issued one tile ahead
+    uint64_t w, wext, ir;
+};
+__device__ __forceinline__ Fast2LaneRaw fast2_lane_issue(const KeySpec& ks, uint64_t W0, int lane) {
+    Fast2LaneRaw r;
+    const uint64_t q = (W0 >> 5) + lane;
+    r.w = q < ks.packed2_words ? __ldg(ks.packed2 + q) : 0ull;
+    r.wext = (lane == 31 && q + 1 < ks.packed2_words) ? __ldg(ks.packed2 + q + 1) : 0ull;
+    const uint64_t qi = (W0 >> 6) + lane;
+    r.ir = (lane <= 16 && qi < ks.irr_words) ? __ldg(ks.irr + qi) : ~0ull;
+    return r;
+}
+__device__ __forceinline__ Fast2Lane fast2_lane_finish(const KeySpec& ks, const Fast2LaneRaw& r, uint64_t W0, int lane,
+                                                       int filter) {
+    Fast2Lane L;
+    L.w = r.w;
+    L.wn = __shfl_down_sync(0xffffffffu, r.w, 1);
+    if (lane == 31) L.wn = r.wext;
+    const uint64_t i0 = __shfl_sync(0xffffffffu, r.ir, lane >> 1);
+    const uint64_t i1 = __shfl_sync(0xffffffffu, r.ir, (lane >> 1) + 1);
+    L.M = (lane & 1) ? ((i0 << 32) | (i1 >> 32)) : i0;  // irregular bits of positions P0 .. P0+63
+    if (filter && !ks.reg_indexed) L.M = ~0ull;         // a regular byte may be filtered: exact path everywhere
+    L.P0 = W0 + 32u * lane;
+    return L;
+}
+__device__ __forceinline__ Fast2Lane fast2_lane_load(const KeySpec& ks, uint64_t W0, int lane, int filter) {
+    return fast2_lane_finish(ks, fast2_lane_issue(ks, W0, lane), W0, lane, filter);
+}
+// key of position P0 + j (j is a compile-time constant in the unrolled callers); filtered suffixes get ~0
+__device__ __forceinline__ uint64_t fast2_lane_key(const KeySpec& ks, const Fast2Lane& L, int j, uint64_t n, int filter) {
+    constexpr uint64_t kWin = ~0ull << (64 - kFast2Symbols);
+    uint64_t key = (j ? ((L.w << (2 * j)) | (L.wn >> ((64 - 2 * j) & 63))) : L.w) & ~3ull;
+    if ((L.M << j) & kWin) {  // irregular symbol in the window (rare): exact key, and the suffix filter
+        const uint64_t p = L.P0 + j;
+        key = 0;
+        if (p < n) key = (filter && !indexed_byte(ks.text[p])) ? ~0ull : first_key_fast2_slow(ks, p);
+    }
+    return key;
+}
+constexpr int kKsTile = (kBlock / 32) * 1024;           // positions per block iteration
+constexpr int kKsSmem = kKsTile * (8 + 2 + 2);          // keys, local positions, ranks
+
+__global__ void __launch_bounds__(kBlock) fast2_first_digit_hist_kernel(KeySpec ks, uint64_t n, int filter,
+                                                                        uint64_t chunk_elems, int shift,
+                                                                        uint32_t* __restrict__ counts) {
     constexpr int WARPS = kBlock / 32;
-    extern __shared__ __align__(16) uint64_t keygen_tr[];  // [WARPS][32][17]
     __shared__ uint32_t hist[WARPS][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < WARPS * 256; i += kBlock) (&hist[0][0])[i] = 0;
     __syncthreads();
-    uint64_t* T = keygen_tr + (size_t)warp * 32 * 17;
     const uint64_t begin = (uint64_t)blockIdx.x * chunk_elems;
     const uint64_t end = begin + chunk_elems < n ? begin + chunk_elems : n;
     for (uint64_t W0 = begin + (uint64_t)warp * 1024; W0 < end; W0 += (uint64_t)WARPS * 1024) {
-        const uint64_t q = (W0 >> 5) + lane;
-        const uint64_t w = q < ks.packed2_words ? __ldg(ks.packed2 + q) : 0ull;
-        uint64_t wn = __shfl_down_sync(0xffffffffu, w, 1);
-        if (lane == 31) wn = q + 1 < ks.packed2_words ? __ldg(ks.packed2 + q + 1) : 0ull;
-        const uint64_t qi = (W0 >> 6) + lane;
-        const uint64_t ir = (lane <= 16 && qi < ks.irr_words) ? __ldg(ks.irr + qi) : ~0ull;
-        const uint64_t i0 = __shfl_sync(0xffffffffu, ir, lane >> 1);
-        const uint64_t i1 = __shfl_sync(0xffffffffu, ir, (lane >> 1) + 1);
-        uint64_t M = (lane & 1) ? ((i0 << 32) | (i1 >> 32)) : i0;  // irregular bits of positions P0 .. P0+63
-        if (filter && !ks.reg_indexed) M = ~0ull;                 // a regular byte may be filtered: exact path everywhere
-        const uint64_t P0 = W0 + 32u * lane;
-        constexpr uint64_t kWin = ~0ull << (64 - kFast2Symbols);
+        const Fast2Lane L = fast2_lane_load(ks, W0, lane, filter);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-#pragma unroll
-            for (int jj = 0; jj < 16; jj++) {
-                const int j = 16 * h + jj;
-                uint64_t key = (j ? ((w << (2 * j)) | (wn >> (64 - 2 * j))) : w) & ~3ull;
-                if ((M << j) & kWin) {  // irregular symbol in the window (rare): exact key, and the suffix filter
-                    const uint64_t p = P0 + j;
-                    key = 0;
-                    if (p < n) key = (filter && !indexed_byte(ks.text[p])) ? ~0ull : first_key_fast2_slow(ks, p);
-                }
-                T[lane * 17 + jj] = key;
-            }
-            __syncwarp();
-            // two rows of 16 keys per store instruction
-#pragma unroll 4
-            for (int it = 0; it < 16; it++) {
-                const int r = 2 * it + (lane >> 4), jj = lane & 15;
-                const uint64_t p = W0 + 32u * r + 16u * h + jj;
-                if (p < n) {
-                    const uint64_t key = T[r * 17 + jj];
-                    keys[p] = key;
-                    pos[p] = (uint32_t)p;
-                    atomicAdd(&hist[warp][(uint32_t)(key >> hist_shift) & 255u], 1u);
-                }
-            }
-            __syncwarp();
+        for (int j = 0; j < 32; j++) {
+            const uint64_t key = fast2_lane_key(ks, L, j, n, filter);
+            if (L.P0 + j < end) atomicAdd(&hist[warp][(uint32_t)(key >> shift) & 255u], 1u);
         }
     }
     __syncthreads();
@@ -322,6 +334,84 @@ __global__ void __launch_bounds__(kBlock) keygen_fast2_kernel(KeySpec ks, uint64
 #pragma unroll
     for (int w2 = 0; w2 < WARPS; w2++) acc += hist[w2][threadIdx.x];
     counts[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kBlock, 2) fast2_keygen_scatter_kernel(KeySpec ks, uint64_t n, int filter,
+                                                                         uint64_t* __restrict__ keys_out,
+                                                                         uint32_t* __restrict__ pos_out,
+                                                                         uint64_t chunk_elems, int shift,
+                                                                         const uint32_t* __restrict__ bases) {
+    constexpr int WARPS = kBlock / 32;
+    extern __shared__ __align__(16) unsigned char ks_smem[];
+    uint64_t* exk = reinterpret_cast<uint64_t*>(ks_smem);                  // records in digit order
+    uint16_t* exl = reinterpret_cast<uint16_t*>(ks_smem + kKsTile * 8);    // their positions, relative to the tile
+    uint16_t* rk = reinterpret_cast<uint16_t*>(ks_smem + kKsTile * 10);    // rank inside (tile, digit), by (j, lane)
+    __shared__ uint32_t cnt[256];      // records per digit in this tile, then the digit's start in the tile
+    __shared__ uint32_t running[256];  // global write cursor of each digit for this block
+    __shared__ uint32_t goff[256];     // global index = goff[d] + tile-local slot (mod 2^32)
+    __shared__ uint32_t warp_tot[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    running[tid] = bases[(uint64_t)tid * gridDim.x + blockIdx.x];
+    const uint64_t begin = (uint64_t)blockIdx.x * chunk_elems;
+    const uint64_t end = begin + chunk_elems < n ? begin + chunk_elems : n;
+    Fast2LaneRaw raw = fast2_lane_issue(ks, begin + (uint64_t)warp * 1024, lane);
+    for (uint64_t tile0 = begin; tile0 < end; tile0 += kKsTile) {
+        const uint32_t count = (end - tile0) < (uint64_t)kKsTile ? (uint32_t)(end - tile0) : (uint32_t)kKsTile;
+        cnt[tid] = 0;
+        __syncthreads();
+        const Fast2Lane L = fast2_lane_finish(ks, raw, tile0 + (uint64_t)warp * 1024, lane, filter);
+        // the next tile's packed words are in flight while this one is ranked, placed and written
+        if (tile0 + kKsTile < end) raw = fast2_lane_issue(ks, tile0 + kKsTile + (uint64_t)warp * 1024, lane);
+        uint16_t* rkw = rk + warp * 1024;
+        // phase 1: rank inside (tile, digit); any order will do
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint64_t key = fast2_lane_key(ks, L, j, n, filter);
+            if (L.P0 + j < end) rkw[j * 32 + lane] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        // thread tid owns digit tid: exclusive scan over the digits
+        const uint32_t c = cnt[tid];
+        uint32_t incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wprefix = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < WARPS; w2++)
+            if (w2 < warp) wprefix += warp_tot[w2];
+        const uint32_t start = wprefix + incl - c;
+        cnt[tid] = start;
+        goff[tid] = running[tid] - start;
+        running[tid] += c;
+        __syncthreads();
+        // phase 2: the keys again (two shifts), placed at start + rank
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (L.P0 + j < end) {
+                const uint64_t key = fast2_lane_key(ks, L, j, n, filter);
+                const uint32_t slot = cnt[(uint32_t)(key >> shift) & 255u] + rkw[j * 32 + lane];
+                exk[slot] = key;
+                exl[slot] = (uint16_t)(warp * 1024 + lane * 32 + j);
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < kKsTile / kBlock; k++) {
+            const uint32_t sl = k * kBlock + tid;
+            if (sl < count) {
+                const uint64_t key = exk[sl];
+                const uint32_t dst = goff[(uint32_t)(key >> shift) & 255u] + sl;
+                keys_out[dst] = key;
+                pos_out[dst] = (uint32_t)(tile0 + exl[sl]);
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // Repetitiveness probe: first keys of every `stride`-th position; after sorting them, the number of adjacent

@@ -285,7 +285,7 @@ using EventPairs = std::vector<std::pair<cudaEvent_t, cudaEvent_t>>;
 template <typename K, typename V>
 bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begin_bit, int end_bit,
                 uint32_t* counts, cudaStream_t stream, uint64_t* launches = nullptr,
-                EventPairs* downsweep_events = nullptr, bool first_counts_ready = false) {
+                EventPairs* downsweep_events = nullptr) {
     constexpr int IPT = Tuning<K, V>::IPT;
     if (n == 0 || end_bit <= begin_bit) return false;
     Plan p = make_plan<K, V>(n);
@@ -300,13 +300,8 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
         K* kout = in_b ? keys_a : keys_b;
         V* vin = in_b ? vals_b : vals_a;
         V* vout = in_b ? vals_a : vals_b;
-        // `first_counts_ready`: the producer of the keys already left the first pass's [digit][block] histogram
-        // in `counts` (same block -> tile assignment as make_plan)
-        if (!(first_counts_ready && bit == begin_bit)) {
-            upsweep_kernel<K, IPT><<<p.grid, BLOCK, 0, stream>>>(kin, n, bit, dmask, counts, p.tiles_per_block);
-            SUFR_KERNEL_CHECK();
-            if (launches) *launches += 1;
-        }
+        upsweep_kernel<K, IPT><<<p.grid, BLOCK, 0, stream>>>(kin, n, bit, dmask, counts, p.tiles_per_block);
+        SUFR_KERNEL_CHECK();
         scan_counts_kernel<<<1, 1024, 0, stream>>>(counts, (uint32_t)RADIX * p.grid);
         SUFR_KERNEL_CHECK();
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -322,7 +317,7 @@ bool sort_pairs(K* keys_a, K* keys_b, V* vals_a, V* vals_b, uint64_t n, int begi
             SUFR_CUDA_CHECK(cudaEventRecord(e1, stream));
             downsweep_events->push_back({e0, e1});
         }
-        if (launches) *launches += 2;
+        if (launches) *launches += 3;
         in_b = !in_b;
     }
     return in_b;
