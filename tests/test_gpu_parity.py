@@ -144,6 +144,24 @@ def test_seed_mask_random(S, mask, name):
     gpu_vs_oracle(S, text, seed_mask=mask, **flags)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(max_query_len=0), dict(seed_mask="1" * 14 + "0" + "1" * 6),
+                                dict(is_dna=True, allow_ambiguity=True)], ids=["protein", "mql", "mask", "dna_amb"])
+def test_general_path_full_word_first_sort(S, kw, monkeypatch):
+    """The general path normally sorts log2(n)+8 key bits first and refines the rest; the whole-word first sort
+    it replaces must give the same result."""
+    rng = random.Random(seed_of("full_word", str(kw)))
+    alphabet = b"ACGTN" if kw.get("is_dna") else b"ACDEFGHIKLMNPQRSTVWY"
+    kw = dict(kw)
+    if "max_query_len" in kw:  # a cap above every LCP: no ties, so the reference's result is well defined
+        text = rand_text(rng, 40000, alphabet)
+        kw["max_query_len"] = int(O.oracle_build(text, num_partitions=4).lcp.max()) + 1
+    else:
+        text = rand_text(rng, 40000, alphabet, repeat_p=0.05)
+    gpu_vs_oracle(S, text, **kw)
+    monkeypatch.setenv("SUFR_B200_DEBUG_FULL_WORD_SORT", "1")
+    gpu_vs_oracle(S, text, **kw)
+
+
 def test_text_without_sentinel(S):
     # library users may pass a text without a trailing '$' (sufr_builder.rs:1044, 1086)
     for t in (b"TTTAGC", b"ACGTNNACGT", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"):
