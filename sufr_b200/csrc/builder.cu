@@ -1397,21 +1397,23 @@ class StreamWriter {
     StreamWriter(int fd, const std::string& path, int device, cudaStream_t stream, size_t slot_bytes = 64u << 20, int nslots = 6,
                  int nworkers = 4)
         : fd_(fd), path_(path), device_(device), stream_(stream), slot_bytes_(slot_bytes) {
-        for (int i = 0; i < nslots; i++) {
-            Slot sl;
-            SUFR_CUDA_CHECK(cudaMallocHost(&sl.buf, slot_bytes_));
-            SUFR_CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
-            slots_.push_back(sl);
-            free_.push_back(i);
+        try {
+            for (int i = 0; i < nslots; i++) {
+                Slot sl{nullptr, nullptr};
+                SUFR_CUDA_CHECK(cudaMallocHost(&sl.buf, slot_bytes_));
+                slots_.push_back(sl);
+                SUFR_CUDA_CHECK(cudaEventCreateWithFlags(&slots_.back().ev, cudaEventDisableTiming));
+                free_.push_back(i);
+            }
+        } catch (...) {  // a constructor that throws runs no destructor: release what was allocated
+            release_slots();
+            throw;
         }
         for (int i = 0; i < nworkers; i++) workers_.emplace_back([this] { work(); });
     }
     ~StreamWriter() {
         try { finish(); } catch (...) {}
-        for (auto& sl : slots_) {
-            cudaFreeHost(sl.buf);
-            cudaEventDestroy(sl.ev);
-        }
+        release_slots();
     }
     // Queue `len` bytes of device memory for file offset `off`; `host_copy` (optional) also receives them.
     void submit(const void* dev, size_t len, uint64_t off, uint8_t* host_copy = nullptr) {
@@ -1456,6 +1458,13 @@ class StreamWriter {
    private:
     struct Slot { void* buf; cudaEvent_t ev; };
     struct Job { int slot; size_t len; uint64_t off; uint8_t* host_copy; };
+    void release_slots() {
+        for (auto& sl : slots_) {
+            if (sl.buf) cudaFreeHost(sl.buf);
+            if (sl.ev) cudaEventDestroy(sl.ev);
+        }
+        slots_.clear();
+    }
     void work() {
         cudaSetDevice(device_);
         for (;;) {
