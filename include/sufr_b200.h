@@ -133,6 +133,28 @@ void sufr_b200_result_free(SufrB200Ctx* ctx, SufrB200Result* result);
 int sufr_b200_patch_seam(SufrB200Ctx* ctx, const SufrB200Args* args, SufrB200Result* result,
                          uint64_t prev_last_suffix);
 
+/* -- verify: full check of a finished DEVICE result against the transformed text, independent of the data
+ *    structures of the build (sufr_b200/csrc/verify.cuh): every SA entry is an indexed position
+ *    (sufr_builder.rs:446-449) and none occurs twice; EVERY adjacent pair is in the order the mode defines and
+ *    every LCP value is the mode's value (full sort; N-run rule :305-307, :701-712; --max-query-len; seed mask).
+ *    Sharded builds: every rank verifies its shard, `has_prev` / `prev_last_suffix` add the seam pair.
+ *    The result is correct iff all error counters are 0 and the ranks' num_suffixes sum to expected_suffixes. */
+typedef struct SufrB200VerifyReport {
+    uint64_t pairs_checked;     /* adjacent pairs compared (num_suffixes - 1, + 1 with has_prev) */
+    uint64_t order_errors;
+    uint64_t lcp_errors;
+    uint64_t out_of_range;      /* SA entries >= text_len */
+    uint64_t not_indexed;       /* SA entries the reference would not index */
+    uint64_t duplicates;        /* positions that occur more than once in this array */
+    uint64_t first_bad_rank;    /* smallest rank with an order / LCP error, UINT64_MAX if none */
+    uint64_t max_lcp;
+    uint64_t lcp_sum;
+    uint64_t expected_suffixes; /* positions of the text the reference indexes */
+    double ms;                  /* device time of the check */
+} SufrB200VerifyReport;
+int sufr_b200_verify(SufrB200Ctx* ctx, const SufrB200Args* args, const SufrB200Result* result, int has_prev,
+                     uint64_t prev_last_suffix, SufrB200VerifyReport* out);
+
 /* -- write: replaces SufrBuilder::write (sufr_builder.rs:817-918), version-6 `.sufr` layout.
  *    Single shard: writes the whole file.  Sharded: every rank calls it with the same path; rank 0
  *    writes header, text and the names tail, every rank pwrites its SA / LCP slice at its offset.

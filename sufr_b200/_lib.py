@@ -87,6 +87,16 @@ class Result(C.Structure):
     ]
 
 
+class VerifyReport(C.Structure):
+    """struct SufrB200VerifyReport"""
+    _fields_ = [(k, C.c_uint64) for k in
+                ("pairs_checked", "order_errors", "lcp_errors", "out_of_range", "not_indexed", "duplicates",
+                 "first_bad_rank", "max_lcp", "lcp_sum", "expected_suffixes")] + [("ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class Sequences(C.Structure):
     """struct SufrB200Sequences"""
     _fields_ = [
@@ -101,7 +111,8 @@ class Sequences(C.Structure):
 # every symbol include/sufr_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "sufr_b200_ctx_create", "sufr_b200_ctx_destroy", "sufr_b200_ctx_reserve", "sufr_b200_ctx_trim",
-    "sufr_b200_build", "sufr_b200_result_free", "sufr_b200_patch_seam", "sufr_b200_write", "sufr_b200_create",
+    "sufr_b200_build", "sufr_b200_result_free", "sufr_b200_patch_seam", "sufr_b200_verify", "sufr_b200_write",
+    "sufr_b200_create",
     "sufr_b200_seed_mask", "sufr_b200_find_lcp_full_offset", "sufr_b200_read_sequence_file",
     "sufr_b200_sequences_free", "sufr_b200_synth_dna", "sufr_b200_last_error", "sufr_b200_abi_version",
     "sufr_b200_device_count",
@@ -140,6 +151,9 @@ def lib():
     L.sufr_b200_result_free.argtypes = [C.c_void_p, C.POINTER(Result)]
     L.sufr_b200_patch_seam.restype = C.c_int
     L.sufr_b200_patch_seam.argtypes = [C.c_void_p, C.POINTER(Args), C.POINTER(Result), C.c_uint64]
+    L.sufr_b200_verify.restype = C.c_int
+    L.sufr_b200_verify.argtypes = [C.c_void_p, C.POINTER(Args), C.POINTER(Result), C.c_int, C.c_uint64,
+                                   C.POINTER(VerifyReport)]
     L.sufr_b200_write.restype = C.c_int
     L.sufr_b200_write.argtypes = [C.POINTER(Args), C.POINTER(Result)]
     L.sufr_b200_create.restype = C.c_int

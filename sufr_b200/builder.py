@@ -279,6 +279,18 @@ class BuildResult:
         _check(_lib.lib().sufr_b200_patch_seam(self._ctx.handle, C.byref(self._cargs.c), C.byref(self.c),
                                                prev_last_suffix))
 
+    def verify(self, prev_last_suffix: Optional[int] = None) -> dict:
+        """Full on-device check of a DEVICE result (sufr_b200_verify): every SA entry indexed and unique, every
+        adjacent pair in order, every LCP value exact.  Returns the report with ``ok`` added; for a sharded
+        build ``ok`` covers this shard only (the caller sums num_suffixes against expected_suffixes)."""
+        rep = _lib.VerifyReport()
+        _check(_lib.lib().sufr_b200_verify(self._ctx.handle, C.byref(self._cargs.c), C.byref(self.c),
+                                           int(prev_last_suffix is not None), int(prev_last_suffix or 0), C.byref(rep)))
+        d = rep.as_dict()
+        errors = d["order_errors"] + d["lcp_errors"] + d["out_of_range"] + d["not_indexed"] + d["duplicates"]
+        d["ok"] = errors == 0 and (self._cargs.c.world_size > 1 or d["expected_suffixes"] == self.num_suffixes)
+        return d
+
     def write(self):
         _check(_lib.lib().sufr_b200_write(C.byref(self._cargs.c), C.byref(self.c)))
 

@@ -36,6 +36,7 @@
 #include "pool.hpp"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "verify.cuh"
 
 namespace sufr {
 
@@ -403,7 +404,7 @@ void Build::encode(const uint8_t* d_raw) {
     }
     if (num_words) {
         // grid: a multiple of the SM count; every block walks its tiles with a two-deep cp.async pipeline
-        uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(num_words, kBlock), (uint64_t)kNumSMs * 6);
+        uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(num_words, kBlock), (uint64_t)num_sms() * 6);
         pack_kernel<<<grid, kBlock, 0, st()>>>(d_text.get(), n, d_lut.get(), bits, pt.K, num_words, d_words.get(),
                                                ks.fast2 ? d_cls2.get() : nullptr, words2, d_packed2.get(),
                                                reinterpret_cast<uint32_t*>(d_irr.get()));
@@ -605,7 +606,7 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
                 static bool attr_set[64] = {};
                 allow_dynamic_smem(fast2_keygen_scatter_kernel, kKsSmem, attr_set);
                 const uint64_t tiles = div_up(n, kKsTile);
-                const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)kNumSMs * 4);
+                const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms() * 4);
                 const uint64_t chunk = div_up(tiles, grid) * kKsTile;
                 const uint32_t used_grid = (uint32_t)div_up(n, chunk);
                 const int shift = 64 - kFast2SortBits;
@@ -693,14 +694,10 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // sorted a 2-bit approximation of the first symbols, so its refinement starts with word 0.
     int word = (fast2 || partial_sort_) ? -1 : 0;
     int final_word = (!fast2 && (uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
-    DevBuf<uint32_t> large;  // fast path: members of runs too long to be ordered inside round 0 (kernels.cuh)
-    if (fast2) {
-        large = dalloc<uint32_t>(r0n / 32 + 1);
-        SUFR_CUDA_CHECK(cudaMemsetAsync(large.get(), 0, (r0n / 32 + 1) * 4, st()));
-    }
-    // the fast path's round 0 is out of place: the ordered records land in the sort's ping-pong partners
-    ViewAll v0{fast2 ? keys_spare_.get() : keys_sorted.get(), fast2 ? pos_spare_.get() : d_sa.get(),
-               fast2 ? large.get() : nullptr, fast2 ? ~0ull : sort_kmask_};
+    // the fast path's round 0 is out of place: the ordered positions land in the sort's ping-pong partner; the
+    // ordered keys are not written (the LCP marks carry the group structure), so the key partner is free already
+    if (fast2) keys_spare_.reset();
+    ViewAll v0{keys_sorted.get(), d_sa.get(), nullptr, sort_kmask_};  // general path only
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, pos, seg;
     {
@@ -724,10 +721,9 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                     wide_ok_ = true;
                 }
             }
-            round0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), keys_spare_.get(),
-                                                                      pos_spare_.get(), r0n, large.get(), d_lcp.get(),
-                                                                      act_slot.get(), act_pos.get(), d_cnt.get(), capacity,
-                                                                      wide_sa_.get(), wide_lcp_.get());
+            round0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), pos_spare_.get(), r0n,
+                                                                      d_lcp.get(), act_slot.get(), act_pos.get(), d_cnt.get(),
+                                                                      capacity, wide_sa_.get(), wide_lcp_.get());
         } else {
             resolve0_append_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks, final_word,
                                                                          sort_kmask_, d_lcp.get(), act_slot.get(), act_pos.get(),
@@ -735,8 +731,8 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         }
         SUFR_KERNEL_CHECK();
         launched();
-        if (fast2) {  // the ordered records are in the partners now
-            keys_sorted = std::move(keys_spare_);
+        if (fast2) {  // the ordered positions are in the partner now
+            keys_sorted.reset();
             d_sa = std::move(pos_spare_);
         }
         if (final_word) {
@@ -766,21 +762,33 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                 wide_m_ = m;
             }
             seg = dalloc<uint32_t>(m);
-            nseg = scan_total(m, SparseSegIn{v0, slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
+            if (fast2) nseg = scan_total(m, LcpSegIn{d_lcp.get(), slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
+            else nseg = scan_total(m, SparseSegIn{v0, slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
         } else {
             // dense (repetitive text): order-preserving compaction by scan
             drop_wide();
             act_slot.reset();
             act_pos.reset();
             DevBuf<unsigned long long> part;
-            ActiveIn<ViewAll> ain{v0, r0n, 0, sentinel_ ? 1 : 0};
-            unsigned long long tot = scan_begin(r0n, ain, scan::SumU64{}, part);
-            m = (uint32_t)tot;
-            nseg = tot >> 32;
-            slot = dalloc<uint32_t>(m);
-            pos = dalloc<uint32_t>(m);
-            seg = dalloc<uint32_t>(m);
-            scan_finish(r0n, ain, scan::SumU64{}, ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()}, part);
+            if (fast2) {
+                LcpActiveIn ain{d_lcp.get(), r0n};
+                unsigned long long tot = scan_begin(r0n, ain, scan::SumU64{}, part);
+                m = (uint32_t)tot;
+                nseg = tot >> 32;
+                slot = dalloc<uint32_t>(m);
+                pos = dalloc<uint32_t>(m);
+                seg = dalloc<uint32_t>(m);
+                scan_finish(r0n, ain, scan::SumU64{}, LcpActiveOut{d_sa.get(), slot.get(), pos.get(), seg.get()}, part);
+            } else {
+                ActiveIn<ViewAll> ain{v0, r0n, 0, sentinel_ ? 1 : 0};
+                unsigned long long tot = scan_begin(r0n, ain, scan::SumU64{}, part);
+                m = (uint32_t)tot;
+                nseg = tot >> 32;
+                slot = dalloc<uint32_t>(m);
+                pos = dalloc<uint32_t>(m);
+                seg = dalloc<uint32_t>(m);
+                scan_finish(r0n, ain, scan::SumU64{}, ActiveOut<ViewAll>{v0, slot.get(), pos.get(), seg.get()}, part);
+            }
         }
     }
     keys_sorted.reset();
@@ -1738,6 +1746,96 @@ int sufr_b200_patch_seam(SufrB200Ctx* c, const SufrB200Args* args, SufrB200Resul
             if (r->index_bits == 32) ((uint32_t*)r->lcp)[0] = (uint32_t)l;
             else ((uint64_t*)r->lcp)[0] = l;
         }
+    });
+}
+
+int sufr_b200_verify(SufrB200Ctx* c, const SufrB200Args* args, const SufrB200Result* r, int has_prev,
+                     uint64_t prev_last_suffix, SufrB200VerifyReport* out) {
+    return guarded([&] {
+        Ctx* ctx = reinterpret_cast<Ctx*>(c);
+        if (!ctx || !args || !r || !out) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (r->memory != SUFR_B200_MEM_DEVICE || !r->text)
+            throw Error(SUFR_B200_ERR_ARGUMENT, "sufr_b200_verify needs a device result (with its transformed text)");
+        SeedMaskInfo mask;
+        const bool has_mask = args->seed_mask && parse_seed_mask(args->seed_mask, mask);
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        const uint64_t n = r->text_len, s = r->num_suffixes;
+        verify::Params P{};
+        P.text = r->text;
+        P.n = n;
+        P.sa = r->sa;
+        P.lcp = r->lcp;
+        P.s = s;
+        P.wide = r->index_bits == 64;
+        P.filter = args->is_dna && !args->allow_ambiguity;
+        P.mode = has_mask ? 2 : (args->has_max_query_len && args->max_query_len > 0 ? 1 : 0);
+        P.q = args->max_query_len;
+        P.has_prev = has_prev ? 1 : 0;
+        P.prev_last = prev_last_suffix;
+        DevBuf<uint32_t> d_maskpos;
+        if (has_mask) {
+            std::vector<uint32_t> mp(mask.positions.begin(), mask.positions.end());
+            d_maskpos = DevBuf<uint32_t>(ctx->pool, mp.size());
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(d_maskpos.get(), mp.data(), mp.size() * 4, cudaMemcpyHostToDevice, st));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st));
+            P.mask_pos = d_maskpos.get();
+            P.weight = (uint32_t)mask.weight;
+        }
+        DevBuf<uint64_t> d_ns, d_ne;
+        if (!has_mask && r->num_n_ranges) {  // find_lcp consults the runs only outside mask mode (sufr_builder.rs:301-307)
+            std::vector<uint64_t> hs(r->num_n_ranges), he(r->num_n_ranges);
+            for (uint64_t i = 0; i < r->num_n_ranges; i++) { hs[i] = r->n_ranges[2 * i]; he[i] = r->n_ranges[2 * i + 1]; }
+            d_ns = DevBuf<uint64_t>(ctx->pool, hs.size());
+            d_ne = DevBuf<uint64_t>(ctx->pool, he.size());
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(d_ns.get(), hs.data(), hs.size() * 8, cudaMemcpyHostToDevice, st));
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(d_ne.get(), he.data(), he.size() * 8, cudaMemcpyHostToDevice, st));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st));
+            P.n_starts = d_ns.get();
+            P.n_ends = d_ne.get();
+            P.num_n_ranges = (uint32_t)r->num_n_ranges;
+        }
+        DevBuf<uint32_t> bitmap(ctx->pool, n / 32 + 2);
+        DevBuf<verify::Report> d_rep(ctx->pool, 1);
+        DevBuf<unsigned long long> d_cnt(ctx->pool, 1);
+        verify::Report init{};
+        init.first_bad_rank = ~0ull;
+        SUFR_CUDA_CHECK(cudaMemsetAsync(bitmap.get(), 0, (n / 32 + 2) * 4, st));
+        SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st));
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(d_rep.get(), &init, sizeof(init), cudaMemcpyHostToDevice, st));
+        EventTimer timer(st);
+        const int t0 = timer.mark();
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, div_up(s, 256)), (uint64_t)num_sms() * 16);
+        if (s) {
+            verify::positions_kernel<<<grid, 256, 0, st>>>(P, bitmap.get(), d_rep.get());
+            SUFR_KERNEL_CHECK();
+            verify::pairs_kernel<<<grid, 256, 0, st>>>(P, d_rep.get());
+            SUFR_KERNEL_CHECK();
+        }
+        if (P.filter && n) {
+            verify::count_indexed_kernel<<<(uint32_t)std::min<uint64_t>(div_up(n, 256 * 16), (uint64_t)num_sms() * 16), 256, 0, st>>>(
+                r->text, n, d_cnt.get());
+            SUFR_KERNEL_CHECK();
+        }
+        const int t1 = timer.mark();
+        verify::Report rep{};
+        unsigned long long cnt = 0;
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&rep, d_rep.get(), sizeof(rep), cudaMemcpyDeviceToHost, st));
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(&cnt, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(st));
+        memset(out, 0, sizeof(*out));
+        out->pairs_checked = rep.pairs_checked;
+        out->order_errors = rep.order_errors;
+        out->lcp_errors = rep.lcp_errors;
+        out->out_of_range = rep.out_of_range;
+        out->not_indexed = rep.not_indexed;
+        out->duplicates = rep.duplicates;
+        out->first_bad_rank = rep.first_bad_rank;
+        out->max_lcp = rep.max_lcp;
+        out->lcp_sum = rep.lcp_sum;
+        out->expected_suffixes = P.filter ? cnt : n;
+        out->ms = timer.ms(t0, t1);
     });
 }
 

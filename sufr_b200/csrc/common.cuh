@@ -25,7 +25,23 @@ struct Error : std::runtime_error {
 
 #define SUFR_KERNEL_CHECK() SUFR_CUDA_CHECK(cudaGetLastError())
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs (fallback when the device cannot be queried)
+
+// SM count of the current device (queried once per device): grids are sized in multiples of it.
+inline int num_sms() {
+    static int sms[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        cudaGetLastError();
+        return kNumSMs;
+    }
+    if (!sms[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms[dev] = v;
+        else { cudaGetLastError(); sms[dev] = kNumSMs; }
+    }
+    return sms[dev];
+}
 
 // Opt a kernel in to more than 48 KB of dynamic shared memory, once per device (the attribute is per device).
 template <typename Kernel>

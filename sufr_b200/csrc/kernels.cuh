@@ -37,7 +37,7 @@ struct CountOnlyU64 {
 
 inline uint32_t grid_for(uint64_t n, int per_thread = 1) {
     uint64_t blocks = div_up(n, (uint64_t)kBlock * per_thread);
-    uint64_t cap = (uint64_t)kNumSMs * 32;  // grid-stride beyond 32 CTAs per SM
+    uint64_t cap = (uint64_t)num_sms() * 32;  // grid-stride beyond 32 CTAs per SM
     if (blocks > cap) blocks = cap;
     return (uint32_t)(blocks ? blocks : 1);
 }
@@ -816,8 +816,7 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
 
 // Fast path, after the 4-pass radix sort on the top kFast2SortBits: group ordering and round 0 in ONE pass over the
 // radix-sorted records.  A run is a maximal sequence of records that tie on the sorted bits.  Runs of 2..8 are
-// ordered by their full 31-symbol keys; members of longer runs are marked in the `large` bitmap and left to the
-// refinement.  A group is then a run of equal canonical keys (fast2_canon): exact ties on all 31 symbols, or
+// ordered by their full 31-symbol keys; longer runs ("large") are left to the refinement as one group.  A group is then a run of equal canonical keys (fast2_canon): exact ties on all 31 symbols, or
 // the members of a large run; everything in a group of size > 1 is collected for the exact refinement (which
 // starts at key word 0).  Boundary LCP = clz(x ^ y) / 2 when neither key contains fill and both neighbours are
 // final (singleton groups), else it is recomputed from the final order (kLcpFixup).  Filtered suffixes (key ~0)
@@ -831,8 +830,10 @@ __global__ void __launch_bounds__(kBlock) resolve0_append_kernel(const uint64_t*
 //            does): boundary LCP / pending / fix-up mark and the unresolved flag; unresolved records are appended
 //            with one global atomic per tile.
 // Runs that are cut off by the staging window are either long enough to be known large or are not adjacent to
-// anything this tile emits.  OUT OF PLACE (the radix sort's ping-pong partners receive the ordered records): a tile
-// reads records that a neighbouring tile orders, so an in-place update would race.
+// anything this tile emits.  OUT OF PLACE (the radix sort's ping-pong partner receives the ordered positions): a tile
+// reads records that a neighbouring tile orders, so an in-place update would race.  The ordered KEYS are not written
+// at all: the LCP marks carry the group structure the refinement needs (kLcpPending <=> the record continues the
+// group of its predecessor), see LcpSegIn / LcpActiveIn.
 constexpr int kR0Tile = 1024, kR0Back = kFast2SmallGroup + 1, kR0Fwd = kFast2SmallGroup;
 constexpr int kR0N = kR0Tile + kR0Back + kR0Fwd;
 constexpr int kR0Steps = (kR0N + 1 + kBlock - 1) / kBlock;
@@ -853,10 +854,8 @@ __device__ __forceinline__ RunExtent run_extent(const uint32_t* hbm, uint32_t a)
 }
 __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ pos,
-                                                              uint64_t* __restrict__ keys_out,
                                                               uint32_t* __restrict__ pos_out,
-                                                              uint64_t s, uint32_t* __restrict__ large,
-                                                              uint32_t* __restrict__ lcp,
+                                                              uint64_t s, uint32_t* __restrict__ lcp,
                                                               uint32_t* __restrict__ act_slot,
                                                               uint32_t* __restrict__ act_pos,
                                                               unsigned long long* __restrict__ act_count,
@@ -927,7 +926,6 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
         // phase 2: LCP / flags of the records this tile owns
         uint32_t act = 0;
         uint32_t apos[kR0Steps];
-        uint64_t* const keys_t = keys_out + g0;
         uint32_t* const pos_t = pos_out + g0;
         uint32_t* const lcp_t = lcp + g0;
 #pragma unroll
@@ -972,13 +970,11 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
             }
             lcp_t[d] = out;
             apos[k] = pb[d];
-            keys_t[d] = k0;
             pos_t[d] = apos[k];
             if (sa64) {  // 64-bit device results: written here, later changes are patched in (Build::refine)
                 sa64[g0 + d] = apos[k];
                 lcp64[g0 + d] = out;
             }
-            if (is_large) atomicOr(&large[(g0 + d) >> 5], 1u << ((g0 + d) & 31));
             if (!head || next_same) act |= 1u << k;
         }
         // append: per-thread count -> warp prefix -> block prefix -> one atomic
@@ -1040,6 +1036,37 @@ __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t 
         }
     }
 }
+
+// Group structure of the fast path after round 0, read off the LCP marks: record j continues the group of record
+// j-1 iff lcp[j] == kLcpPending; it is unresolved iff it continues a group or its successor does.
+struct LcpSegIn {  // segment ids of the slot-sorted unresolved list
+    const uint32_t* lcp;
+    const uint32_t* slot;
+    __device__ uint32_t operator()(uint64_t a) const { return lcp[slot[a]] != kLcpPending ? 1u : 0u; }
+};
+struct LcpActiveIn {  // dense variant: order-preserving compaction of all unresolved records
+    const uint32_t* lcp;
+    uint64_t m;
+    __device__ unsigned long long operator()(uint64_t i) const {
+        const bool head = lcp[i] != kLcpPending;
+        const bool next_same = i + 1 < m && lcp[i + 1] == kLcpPending;
+        return (!head || next_same) ? (1ull | ((unsigned long long)head << 32)) : 0ull;
+    }
+};
+struct LcpActiveOut {
+    const uint32_t* pos;
+    uint32_t* new_slot;
+    uint32_t* new_pos;
+    uint32_t* new_seg;
+    __device__ void operator()(uint64_t i, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            const uint32_t a = (uint32_t)incl - 1;
+            new_slot[a] = (uint32_t)i;
+            new_pos[a] = pos[i];
+            new_seg[a] = (uint32_t)(incl >> 32) - 1;
+        }
+    }
+};
 
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
 // previous SA slot's key
