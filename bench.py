@@ -8,11 +8,16 @@ uniform ACGT, '%' between records, '$' at the end; u64 SA/LCP as the config name
   value : text already resident in HBM, SA/LCP left in HBM (device-timed, whole job over all ranks)
   e2e   : the same build through the C ABI with HOST buffers -- pinned text copied H2D, SA/LCP/text
           copied D2H -- all inside the timed region
-  roofline     : the dominant kernel (radix-sort downsweep), CUDA-event timed per launch inside the step
+  roofline     : the dominant kernel (radix-sort scatter pass), CUDA-event timed per launch inside the step
   cpu_baseline : the oracle restatement of the reference's rayon path on a bounded prefix of the same text
+  verify       : FULL on-device check of the last timed result (sufr_b200_verify): every SA entry indexed and
+                 unique, every adjacent pair in order, every LCP exact -- pairs = num_suffixes - 1
+  configs      : the other BASELINE.json configs (1, 3, 4, 5 and the repetitive variant 2b) at their full sizes
+                 on one GPU, each with its own value, job roofline and full verification (--no-configs to skip)
 
 `--impl reference` times the reference's CPU algorithm (oracle port; the Rust reference cannot be compiled
-in this image) with all host threads on a bounded sample of the same workload.
+in this image) with the flags the workload names (-n 16, u64 indices) on a bounded sample of the same
+workload; the sample size is part of `config` in BOTH arms (reference_arm_sample_bases).
 
 N > 1 (torchrun): the text is replicated, rank r builds key-range shard r (no data-path collective), one
 all_gather of (count, first, last) repairs the seam LCPs.  Fixed total work => "scaling": "strong".
@@ -138,33 +143,43 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples), "source": self.source}
 
 
-def oracle_run(sample: bytes, threads: int, partitions: int):
+def oracle_run(sample: bytes, threads: int, partitions: int, index_bits: int = 64):
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle as O
     t0 = time.perf_counter()
-    r = O.oracle_build(sample, is_dna=True, num_partitions=partitions, threads=threads, index_bits=32)
+    r = O.oracle_build(sample, is_dna=True, num_partitions=partitions, threads=threads, index_bits=index_bits)
     dt = time.perf_counter() - t0
     return r, dt
 
 
+def reference_sample_bases(args):
+    """Bases per step of the reference arm: bounded so that (steps + warmup) builds end within a few minutes
+    at the ~25 M suffixes/s the port reaches, at most 1 Gbp."""
+    if args.cpu_sample:
+        return min(args.cpu_sample, args.bases)
+    budget_s, rate = 200.0, 25e6
+    per_step = int(budget_s * rate / max(1, args.steps + args.warmup))
+    return int(max(32_000_000, min(1_000_000_000, per_step, args.bases)))
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU algorithm (oracle port) on the box's host cores."""
+    """Reference arm: the reference's CPU algorithm (oracle port) on the box's host cores, flags as the workload
+    names them (-n 16, u64 SA / LCP)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     text_len, starts = record_layout(args.bases)
-    sample_n = min(args.cpu_sample, text_len)
+    sample_n = reference_sample_bases(args)
     sample = synth_prefix_numpy(sample_n, text_len, starts)
     if sample_n < text_len:
         sample = sample[:-1] + b"$"
-    parts = max(16, 4 * cores)
     for _ in range(args.warmup):
-        oracle_run(sample, cores, parts)
+        oracle_run(sample, cores, 16, args.index_bits)
     t = 0.0
     nsuf = 0
     for _ in range(args.steps):
-        r, dt = oracle_run(sample, cores, parts)
+        r, dt = oracle_run(sample, cores, 16, args.index_bits)
         t += dt
         nsuf += r.num_suffixes
     value = nsuf / t
@@ -174,8 +189,10 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, text_len),
         "cpu_baseline": {"value": value, "unit": "suffixes/s", "cores": cores, "kind": "port",
-                         "sample": f"first {sample_n} bytes of the workload text (u32 indices, -n {parts}), "
-                                   f"oracle restatement of sufr_builder.rs with {cores} threads, partitions in RAM"},
+                         "sample": f"every step builds the first {sample_n} bytes of the workload text "
+                                   f"(u{args.index_bits} indices, -n 16 as the workload names it: the sort phase runs "
+                                   f"16 partitions in parallel), oracle restatement of sufr_builder.rs with {cores} "
+                                   f"threads, partitions kept in RAM"},
         "e2e": {"value": value, "unit": "suffixes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -185,7 +202,7 @@ def run_reference(args):
 def workload_config(args, text_len):
     return {"workload": f"sufr create --dna, {args.bases} bp synthetic iid ACGT in 24 records (BASELINE configs[1]), "
                         f"u{args.index_bits} SA+LCP", "text_len": text_len, "index_bits": args.index_bits,
-            "flags": "--dna -n 16", "seed": SEED,
+            "flags": "--dna -n 16", "seed": SEED, "reference_arm_sample_bases": reference_sample_bases(args),
             "l2_policy": "inputs (>= 3 GB text, >= 37 GB key/position arrays) are far larger than the 126 MB L2"}
 
 
@@ -197,13 +214,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bases", type=int, default=3_100_000_000)
     ap.add_argument("--index-bits", type=int, default=64, choices=[32, 64])
-    ap.add_argument("--cpu-sample", type=int, default=32_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="bases per step of the reference arm (0 = as many as fit ~200 s over steps + warmup, <= 1 Gbp)")
+    ap.add_argument("--cpu-baseline-sample", type=int, default=400_000_000,
+                    help="bases of the one cpu_baseline build inside our own arm (about 15-20 s of CPU work)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (1, 3, 4, 5, 2b)")
+    ap.add_argument("--configs", default="config1,config3,config4,config5,config2b")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--verify", type=int, default=4000, help="sampled SA/LCP checks after the timed region")
-    ap.add_argument("--repetitive", action="store_true",
-                    help="also time the repetitive variant (config 2b, generated on the host: adds ~1 min)")
+    ap.add_argument("--verify", type=int, default=1, help="0 = skip the full on-device verification of the last result")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
@@ -242,13 +262,12 @@ def main():
     def step_device():
         r = S.build(bargs, index_bits=args.index_bits, ctx=ctx, result_memory=S.MEM_DEVICE,
                     device_text=(d_text.data_ptr(), text_len), rank=rank, world_size=world)
-        if world > 1:
-            finish_shard(r)
-        return r
+        meta = finish_shard(r) if world > 1 else None
+        return r, meta
 
     # ---------------- value: resident text -> resident SA/LCP
     for _ in range(args.warmup):
-        step_device().free()
+        step_device()[0].free()
     barrier()
     results = []
     try:
@@ -258,7 +277,7 @@ def main():
     with ClockSampler(local_rank, gpu_uuid) as clocks:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            r = step_device()
+            r, last_meta = step_device()
             results.append((r.num_suffixes, r.total_suffixes, r.timings, r.kernel_launches))
             last = r
             if _ + 1 < args.steps:
@@ -274,8 +293,8 @@ def main():
     tm = results[-1][2]
     launches = sum(x[3] for x in results)
 
-    # ---------------- sampled verification of the last result (outside the timed region)
-    verify = verify_sample(last, d_text, args.verify, rank, world) if args.verify else None
+    # ---------------- FULL verification of the last timed result on the device (outside the timed region)
+    verify = verify_full(last, last_meta, rank, world, dev) if args.verify else None
     last.free()
 
     # ---------------- e2e: host text in, host SA/LCP out, copies inside the timed region
@@ -287,20 +306,23 @@ def main():
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:
         cores = os.cpu_count() or 1
-        sample_n = min(args.cpu_sample, text_len)
+        sample_n = min(args.cpu_baseline_sample, text_len)
         sample = d_text[:sample_n].cpu().numpy().tobytes()
         if sample_n < text_len:
             sample = sample[:-1] + b"$"
-        parts = max(16, 4 * cores)
-        r, dt = oracle_run(sample, cores, parts)
+        r, dt = oracle_run(sample, cores, 16, args.index_bits)
         cpu = {"value": r.num_suffixes / dt, "unit": "suffixes/s", "cores": cores, "kind": "port",
-               "sample": f"first {sample_n} bytes of the workload text (u32 indices, -n {parts}); oracle "
-                         f"restatement of sufr_builder.rs, {cores} threads, partitions in RAM; {dt:.2f} s"}
+               "sample": f"one build of the first {sample_n} bytes of the workload text (u{args.index_bits} indices, "
+                         f"-n 16 as the workload names it); oracle restatement of sufr_builder.rs, {cores} threads, "
+                         f"partitions in RAM; {dt:.2f} s"}
+    del d_text
+    torch.cuda.empty_cache()
 
-    # ---------------- repetitive variant of the same workload (BASELINE: "random and repetitive FASTA"), N=1 only
-    variants = None
-    if args.repetitive and world == 1:
-        variants = {"repetitive": run_repetitive(args, S, ctx, dev)}
+    # ---------------- the other BASELINE configs at full size (N=1 only): value, job roofline, full verification
+    configs = None
+    if not args.no_configs and world == 1:
+        configs = run_configs(args, S, ctx, dev)
+    variants = {"repetitive": configs["config2b"]} if configs and "config2b" in configs else None
 
     if rank == 0:
         peaks = {}
@@ -321,7 +343,7 @@ def main():
             "config": workload_config(args, text_len),
             "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "rsort::downsweep_kernel<u64,u32> (main sort)",
+            "roofline": {"bound": "hbm", "kernel": "osort::onesweep_kernel<u64,u32,512,16> = radix scatter pass of the main sort",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                          "traffic": traffic_estimate(tm["dominant_kernel_bytes"]), "traffic_source": TRAFFIC_SOURCE,
@@ -332,6 +354,7 @@ def main():
                                  "frac": job_bytes * args.steps / elapsed / 1e9 / world / peak,
                                  "note": "A = n + 2*s*sizeof(T) per SURVEY 8(d), per GPU"}},
             "cpu_baseline": cpu,
+            "configs": configs,
             "variants": variants,
             "phases_ms": {k: v for k, v in tm.items() if k.endswith("_ms")},
             "verify": verify,
@@ -351,73 +374,98 @@ def traffic_estimate(algorithmic_bytes):
     return algorithmic_bytes * (2.781094 + 2.685538) / 4.800000576
 
 
-def run_repetitive(args, S, ctx, dev):
-    """One warm-up + two timed device-resident builds of workloads.config2_repetitive at the same size."""
+FULL_SIZES = {"config1": 10_000_000, "config2b": 3_100_000_000, "config3": 1_000_000_000,
+              "config4": 500_000_000, "config5": 1_000_000_000}
+CONFIG_NOTES = {
+    "config1": "BASELINE configs[0]: sufr create --dna -n 16, 10 Mbp iid ACGT, u32",
+    "config2b": "BASELINE configs[1], repetitive variant: ~50 % of the bases are mutated copies of earlier 0.3-6 kb "
+                "segments, some N / soft-masked stretches, u64",
+    "config3": "BASELINE configs[2]: protein alphabet, 1 G residues in 10 000 records, --max-query-len 32, u32",
+    "config4": "BASELINE configs[3]: --dna --seed-mask 1101101101 on 500 Mbp (the reference rejects the mask together "
+               "with --max-query-len, so the cap is dropped), u32",
+    "config5": "BASELINE configs[4]: --dna --allow-ambiguity --ignore-softmask, 1 Gbp tandem repeats / low entropy / "
+               "soft-masked and N runs, u32",
+}
+
+
+def run_configs(args, S, ctx, dev):
+    """One warm-up + two timed device-resident builds of every other BASELINE config at its full size (scaled with
+    --bases when the headline is scaled), each followed by the full on-device verification."""
     import torch
     import workloads
-    sys.path.insert(0, str(ROOT / "tools"))
-    w = workloads.config2_repetitive(args.bases)
-    t = torch.frombuffer(bytearray(w.text), dtype=torch.uint8).to(dev)
-    bargs = S.SufrBuilderArgs(text=b"", is_dna=True, sequence_starts=w.sequence_starts, sequence_names=w.sequence_names)
-    times, last = [], None
-    for i in range(3):
-        torch.cuda.synchronize()
+    peak = 6650.0
+    try:
+        peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", peak))
+    except Exception:
+        pass
+    scale = min(1.0, args.bases / 3_100_000_000)
+    out = {}
+    for name in [c for c in args.configs.split(",") if c]:
+        size = max(100_000, int(FULL_SIZES[name] * scale))
         t0 = time.perf_counter()
-        r = S.build(bargs, index_bits=args.index_bits, ctx=ctx, result_memory=S.MEM_DEVICE,
-                    device_text=(t.data_ptr(), t.numel()))
-        torch.cuda.synchronize()
-        if i:
-            times.append(time.perf_counter() - t0)
-        info = (r.num_suffixes, int(r.c.refine_rounds), int(r.c.doubling_rounds), r.timings)
-        # against the TRANSFORMED text the index is built on (soft-masked stretches are upper-cased)
-        v = verify_sample(r, r.text_tensor(), 1000, 0, 2) if i == 2 else None
-        r.free()
-    ms = 1e3 * sum(times) / len(times)
-    return {"workload": "config 2b: ~50 % of the bases are mutated copies of earlier 0.3-6 kb segments, some N / "
-                        "soft-masked stretches", "ms_per_step": ms, "value": info[0] / (ms * 1e-3),
-            "unit": "suffixes/s", "refine_rounds": info[1], "doubling_rounds": info[2],
-            "phases_ms": {k: v for k, v in info[3].items() if k.endswith("_ms")}, "verify": v}
-
-
-def verify_sample(res, d_text, k, rank, world):
-    """Size-independent checks at full size: the shard's SA holds distinct positions in suffix order and
-    the LCP values are exact, on k sampled adjacent pairs (compared on the host from text windows)."""
-    import torch
-    s = res.num_suffixes
-    if s < 2:
-        return {"pairs": 0}
-    sa, lcp = res.sa_tensor(), res.lcp_tensor()
-    g = torch.Generator(device="cpu")
-    g.manual_seed(1234 + rank)
-    j = torch.randint(1, s, (k,), generator=g).to(sa.device)
-    # u32 results are viewed as int32 tensors: positions >= 2^31 come out negative, mask them back
-    wrap = 0xFFFFFFFF if sa.dtype == torch.int32 else 0x7FFFFFFFFFFFFFFF
-    a = sa[j - 1].cpu().numpy().astype(np.int64) & wrap
-    b = sa[j].cpu().numpy().astype(np.int64) & wrap
-    l = lcp[j].cpu().numpy().astype(np.int64) & wrap
-    n = d_text.numel()
-    W = 256
-    bad = 0
-    for x, y, ll in zip(a.tolist(), b.tolist(), l.tolist()):
-        ta = bytes(d_text[x:min(n, x + W)].cpu().numpy().tobytes())
-        tb = bytes(d_text[y:min(n, y + W)].cpu().numpy().tobytes())
-        c = 0
-        while c < len(ta) and c < len(tb) and ta[c] == tb[c]:
-            c += 1
-        if c >= W:
-            continue  # deeper than the window: skip
-        ok_order = ta[c:c + 1] < tb[c:c + 1] if c < len(ta) and c < len(tb) else len(ta) < len(tb)
-        if not ok_order or c != ll:
-            bad += 1
-    out = {"pairs": k, "mismatches": bad}
-    if world == 1:
-        tot = int(sa.sum(dtype=torch.int64).item())
-        if sa.dtype == torch.int32:
-            tot += int((sa < 0).sum().item()) << 32
-        # all positions except the delimiters ('%' is not indexed under --dna)
-        expect = n * (n - 1) // 2 - int(torch.nonzero(d_text == ord("%")).sum().item())
-        out["position_sum_ok"] = (tot == expect)
+        w = workloads.ALL[name](size)
+        gen_s = time.perf_counter() - t0
+        t = torch.frombuffer(bytearray(w.text), dtype=torch.uint8).to(dev)
+        bargs = S.SufrBuilderArgs(text=b"", sequence_starts=w.sequence_starts, sequence_names=w.sequence_names, **w.flags)
+        times, info, ver = [], None, None
+        for i in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = S.build(bargs, index_bits=w.index_bits, ctx=ctx, result_memory=S.MEM_DEVICE,
+                        device_text=(t.data_ptr(), t.numel()))
+            torch.cuda.synchronize()
+            if i:
+                times.append(time.perf_counter() - t0)
+            info = (r.num_suffixes, int(r.c.refine_rounds), int(r.c.doubling_rounds), r.timings, r.kernel_launches)
+            if i == 2 and args.verify:
+                ver = r.verify()
+            r.free()
+        ms = 1e3 * sum(times) / len(times)
+        job_bytes = t.numel() + 2 * info[0] * (w.index_bits // 8)
+        out[name] = {"workload": CONFIG_NOTES[name], "text_len": t.numel(), "num_suffixes": info[0],
+                     "index_bits": w.index_bits, "flags": {k: v for k, v in w.flags.items()},
+                     "ms_per_step": ms, "value": info[0] / (ms * 1e-3), "unit": "suffixes/s",
+                     "refine_rounds": info[1], "doubling_rounds": info[2], "gpu_launches_per_step": info[4],
+                     "phases_ms": {k: v for k, v in info[3].items() if k.endswith("_ms")},
+                     "roofline_job": {"algorithmic_bytes": job_bytes, "achieved": job_bytes / (ms * 1e-3) / 1e9,
+                                      "frac": job_bytes / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s"},
+                     "verify": verify_summary(ver, info[0]) if ver else None, "generate_s": round(gen_s, 1)}
+        del t
+        torch.cuda.empty_cache()
+        ctx.trim()
     return out
+
+
+def verify_summary(rep, total_suffixes):
+    """Bench-line form of a SufrB200VerifyReport."""
+    errors = rep["order_errors"] + rep["lcp_errors"] + rep["out_of_range"] + rep["not_indexed"] + rep["duplicates"]
+    return {"method": "sufr_b200_verify: every SA entry indexed + unique (bitmap), every adjacent pair compared on the "
+                      "text bytes (order + exact LCP)",
+            "pairs": rep["pairs_checked"], "mismatches": rep["order_errors"] + rep["lcp_errors"],
+            "order_errors": rep["order_errors"], "lcp_errors": rep["lcp_errors"],
+            "position_errors": rep["out_of_range"] + rep["not_indexed"] + rep["duplicates"],
+            "suffixes": total_suffixes, "expected_suffixes": rep["expected_suffixes"],
+            "count_ok": rep["expected_suffixes"] == total_suffixes, "max_lcp": rep["max_lcp"],
+            "ok": errors == 0 and rep["expected_suffixes"] == total_suffixes, "ms": rep["ms"]}
+
+
+def verify_full(res, meta, rank, world, dev):
+    """Full verification of the last timed result: every rank checks its shard (with the seam pair), the error
+    counters are summed over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from sufr_b200.distributed import previous_last_suffix
+    prev = previous_last_suffix(meta, rank) if (world > 1 and meta) else None
+    rep = res.verify(prev if res.num_suffixes else None)
+    keys = ["pairs_checked", "order_errors", "lcp_errors", "out_of_range", "not_indexed", "duplicates", "lcp_sum"]
+    vals = torch.tensor([rep[k] for k in keys] + [res.num_suffixes], dtype=torch.int64, device=dev)
+    mx = torch.tensor([rep["max_lcp"], int(rep["ms"] * 1000)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    tot = {k: int(v) for k, v in zip(keys, vals.tolist()[:-1])}
+    tot.update(expected_suffixes=rep["expected_suffixes"], max_lcp=int(mx[0].item()), ms=mx[1].item() / 1000.0)
+    return verify_summary(tot, int(vals[-1].item()))
 
 
 def run_e2e(args, S, ctx, d_text, text_len, bargs, rank, world, dev, barrier):

@@ -150,6 +150,10 @@ typedef struct SufrB200VerifyReport {
     uint64_t max_lcp;
     uint64_t lcp_sum;
     uint64_t expected_suffixes; /* positions of the text the reference indexes */
+    uint64_t deferred_pairs;    /* pairs sharing >= 2048 bytes: settled by a second pass, see method */
+    uint32_t method;            /* 0 direct comparison only; 1 deferred pairs compared directly without a bound;
+                                   2 deferred pairs by successor ranks (inverse suffix array) + Kasai LCP in text order */
+    uint32_t reserved;
     double ms;                  /* device time of the check */
 } SufrB200VerifyReport;
 int sufr_b200_verify(SufrB200Ctx* ctx, const SufrB200Args* args, const SufrB200Result* result, int has_prev,

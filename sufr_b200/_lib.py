@@ -91,7 +91,8 @@ class VerifyReport(C.Structure):
     """struct SufrB200VerifyReport"""
     _fields_ = [(k, C.c_uint64) for k in
                 ("pairs_checked", "order_errors", "lcp_errors", "out_of_range", "not_indexed", "duplicates",
-                 "first_bad_rank", "max_lcp", "lcp_sum", "expected_suffixes")] + [("ms", C.c_double)]
+                 "first_bad_rank", "max_lcp", "lcp_sum", "expected_suffixes", "deferred_pairs")] + \
+               [("method", C.c_uint32), ("reserved", C.c_uint32), ("ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -132,6 +132,10 @@ class _CArgs:
         self.c.ignore_softmask = int(a.ignore_softmask)
         self._starts = np.asarray(list(a.sequence_starts), dtype=np.uint64)
         self.c.sequence_starts = self._starts.ctypes.data if len(self._starts) else None
+        if len(a.sequence_names) != len(a.sequence_starts):
+            # the C ABI carries ONE count for both arrays (make_sufr_frame reads num_sequences entries of each)
+            raise SufrError(_lib.ERR_ARGUMENT, f"sequence_names has {len(a.sequence_names)} entries but "
+                                               f"sequence_starts has {len(a.sequence_starts)}")
         names = [s.encode() for s in a.sequence_names]
         self._names = (C.c_char_p * max(1, len(names)))(*names)
         self.c.sequence_names = self._names

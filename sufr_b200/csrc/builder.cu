@@ -221,6 +221,7 @@ class Build {
     bool has_mask = false;
     bool filter_active = false;
     uint32_t alphabet = 0;
+    uint32_t code_n_ = 0;  // packed-text code of 'N' (0 = the text has none)
     uint32_t refine_rounds = 0, doubling_rounds = 0;
 
     DevBuf<uint8_t> d_text;     // transformed text
@@ -340,6 +341,7 @@ void Build::encode(const uint8_t* d_raw) {
     uint8_t lut[256];
     alphabet = 0;
     for (int b = 0; b < 256; b++) lut[b] = present[b] ? (uint8_t)(++alphabet) : 0;
+    code_n_ = lut['N'];
     uint32_t bits = (uint32_t)bits_for(alphabet);
     PackedText& pt = ks.pt;
     pt.n = n;
@@ -522,6 +524,16 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
             for (uint32_t b = 0; b < bins && g < world; b++) {
                 acc += hist[b];
                 while (g < world && acc * world >= total * g) cut[g++] = b + 1;
+            }
+            // N-run rule (sufr_builder.rs:305-307, :701-712): suffixes inside recorded runs with equal (run length,
+            // next byte) form tie chains that are re-ordered by position AFTER the sort.  A chain N^r X.. with r < 4
+            // spans several histogram bins, so no cut may fall inside the range of N-prefixed keys: every chain then
+            // lives on one rank (also when a rank falls back to the unsharded build and slices its range out).
+            // On the 2-bit fast path all N-prefixed suffixes share one key, hence one bin.
+            if (ks.num_n_ranges && !ks.fast2 && code_n_ && ks.pt.bits <= hbits) {
+                const uint32_t nlo = code_n_ << (hbits - ks.pt.bits), nhi = (code_n_ + 1) << (hbits - ks.pt.bits);
+                for (int k = 1; k < world; k++)
+                    if (cut[k] > nlo && cut[k] < nhi) cut[k] = nlo;
             }
             cut_b0_ = cut[args.rank];
             cut_b1_ = cut[args.rank + 1];
@@ -1243,9 +1255,25 @@ void Build::run(SufrB200Result* out) {
         int e0 = timer.mark();
         // sharded builds: only rank 0 returns the transformed text (it writes the text section of the file)
         const bool want_text = args.world_size <= 1 || args.rank == 0;
-        owner->text = want_text ? ctx.pinned.get(n) : nullptr;
-        owner->sa = ctx.pinned.get(s * w);
-        owner->lcp = ctx.pinned.get(s * w);
+        // a CUDA error below must not strand the page-locked buffers in the cache's lent-out list
+        struct PinnedGuard {
+            PinnedCache& cache;
+            std::vector<void*> held;
+            std::vector<cudaEvent_t> events;
+            bool keep = false;
+            void* get(size_t bytes) { void* p = cache.get(bytes); held.push_back(p); return p; }
+            ~PinnedGuard() {
+                for (auto e : events) cudaEventDestroy(e);
+                if (!keep) for (void* p : held) cache.put(p);
+            }
+        } pinned{ctx.pinned};
+        owner->text = want_text ? pinned.get(n) : nullptr;
+        owner->sa = pinned.get(s * w);
+        owner->lcp = pinned.get(s * w);
+        struct OwnerReset {  // the buffers go back through the guard, not through a half-built owner
+            ResultOwner* o; bool keep = false;
+            ~OwnerReset() { if (!keep) { o->text = o->sa = o->lcp = nullptr; } }
+        } owner_reset{owner.get()};
         int e1 = timer.mark();
         if (compact) {
             int hw = (int)std::thread::hardware_concurrency();
@@ -1253,6 +1281,7 @@ void Build::run(SufrB200Result* out) {
             // 1. LCP bytes + exceptions, widened on the host while the suffix array is in flight
             d2h_bytes_ += s + exc_count * 8 + s * 4 + (want_text ? n : 0);
             uint8_t* h8 = (uint8_t*)ctx.pinned.get(s);
+            struct Scratch8 { PinnedCache& c; void* p; ~Scratch8() { if (p) c.put(p); } } h8_guard{ctx.pinned, h8};
             std::vector<uint32_t> eidx(exc_count), eval(exc_count);
             SUFR_CUDA_CHECK(cudaMemcpyAsync(h8, d_lcp8.get(), s, cudaMemcpyDeviceToHost, st()));
             if (exc_count) {
@@ -1286,28 +1315,27 @@ void Build::run(SufrB200Result* out) {
             if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
             if (index_bits_ == 64) {
                 uint32_t* h32 = (uint32_t*)ctx.pinned.get(s * 4);
+                Scratch8 h32_guard{ctx.pinned, h32};
                 constexpr int kChunks = 8;
-                cudaEvent_t done[kChunks];
                 for (int c = 0; c < kChunks; c++) {
                     uint64_t lo = s * (uint64_t)c / kChunks, hi = s * (uint64_t)(c + 1) / kChunks;
                     if (hi > lo)
                         SUFR_CUDA_CHECK(cudaMemcpyAsync(h32 + lo, d_sa.get() + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, st()));
-                    SUFR_CUDA_CHECK(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
-                    SUFR_CUDA_CHECK(cudaEventRecord(done[c], st()));
+                    cudaEvent_t ev = nullptr;
+                    SUFR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    pinned.events.push_back(ev);
+                    SUFR_CUDA_CHECK(cudaEventRecord(ev, st()));
                 }
                 for (int c = 0; c < kChunks; c++) {
                     uint64_t lo = s * (uint64_t)c / kChunks, hi = s * (uint64_t)(c + 1) / kChunks;
-                    SUFR_CUDA_CHECK(cudaEventSynchronize(done[c]));
-                    cudaEventDestroy(done[c]);
+                    SUFR_CUDA_CHECK(cudaEventSynchronize(pinned.events[c]));
                     if (hi > lo) host_widen(h32 + lo, (uint64_t*)owner->sa + lo, hi - lo, threads);
                 }
-                ctx.pinned.put(h32);
             } else {
                 SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa.get(), s * 4, cudaMemcpyDeviceToHost, st()));
             }
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
             lcp_worker.join();
-            ctx.pinned.put(h8);
         } else {
             d2h_bytes_ += 2 * s * w + (want_text ? n : 0);
             if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));
@@ -1320,6 +1348,8 @@ void Build::run(SufrB200Result* out) {
         SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
         (void)e0;
         tm.d2h_ms = timer.ms(e1, e2);
+        pinned.keep = true;  // ownership moves to the returned result
+        owner_reset.keep = true;
     }
     if (!n_ranges_host.empty()) {
         owner->n_ranges = (uint64_t*)malloc(n_ranges_host.size() * 8);
@@ -1807,11 +1837,40 @@ int sufr_b200_verify(SufrB200Ctx* c, const SufrB200Args* args, const SufrB200Res
         EventTimer timer(st);
         const int t0 = timer.mark();
         const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, div_up(s, 256)), (uint64_t)num_sms() * 16);
+        DevBuf<uint32_t> defer_bits(ctx->pool, s / 32 + 2);
+        SUFR_CUDA_CHECK(cudaMemsetAsync(defer_bits.get(), 0, (s / 32 + 2) * 4, st));
+        int method = 0;
         if (s) {
             verify::positions_kernel<<<grid, 256, 0, st>>>(P, bitmap.get(), d_rep.get());
             SUFR_KERNEL_CHECK();
-            verify::pairs_kernel<<<grid, 256, 0, st>>>(P, d_rep.get());
+            verify::pairs_kernel<<<grid, 256, 0, st>>>(P, d_rep.get(), defer_bits.get(), 0);
             SUFR_KERNEL_CHECK();
+            verify::Report mid{};
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(&mid, d_rep.get(), sizeof(mid), cudaMemcpyDeviceToHost, st));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (mid.deferred) {
+                // deep repeats.  Full sort with every position present in this array: linear-time proof through the
+                // inverse suffix array; otherwise (filtered / sharded / capped keys) the deferred pairs directly.
+                const bool linear = P.mode == 0 && s == n && !has_prev && mid.duplicates == 0 && mid.out_of_range == 0 &&
+                                    n <= 0xFFFFFFFFull;
+                if (linear) {
+                    method = 2;
+                    DevBuf<uint32_t> isa(ctx->pool, n + 1);
+                    verify::isa_kernel<<<grid, 256, 0, st>>>(P, isa.get());
+                    SUFR_KERNEL_CHECK();
+                    verify::order_by_rank_kernel<<<grid, 256, 0, st>>>(P, isa.get(), defer_bits.get(), d_rep.get());
+                    SUFR_KERNEL_CHECK();
+                    const uint64_t chunks = div_up(n, verify::kKasaiChunk);
+                    verify::kasai_kernel<<<(uint32_t)std::max<uint64_t>(1, div_up(chunks, 256)), 256, 0, st>>>(
+                        P, isa.get(), defer_bits.get(), d_rep.get());
+                    SUFR_KERNEL_CHECK();
+                    SUFR_CUDA_CHECK(cudaStreamSynchronize(st));
+                } else {
+                    method = 1;
+                    verify::pairs_kernel<<<grid, 256, 0, st>>>(P, d_rep.get(), defer_bits.get(), 1);
+                    SUFR_KERNEL_CHECK();
+                }
+            }
         }
         if (P.filter && n) {
             verify::count_indexed_kernel<<<(uint32_t)std::min<uint64_t>(div_up(n, 256 * 16), (uint64_t)num_sms() * 16), 256, 0, st>>>(
@@ -1835,6 +1894,8 @@ int sufr_b200_verify(SufrB200Ctx* c, const SufrB200Args* args, const SufrB200Res
         out->max_lcp = rep.max_lcp;
         out->lcp_sum = rep.lcp_sum;
         out->expected_suffixes = P.filter ? cnt : n;
+        out->deferred_pairs = rep.deferred;
+        out->method = (uint32_t)method;
         out->ms = timer.ms(t0, t1);
     });
 }

@@ -71,6 +71,11 @@ void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const std::st
 SufrFrame make_sufr_frame(const SufrB200Args& args, uint32_t index_bits, uint64_t text_len, uint64_t total_suffixes) {
     SufrFrame f;
     const size_t w = index_bits / 8;
+    if (args.num_sequences && !args.sequence_starts)
+        throw Error(SUFR_B200_ERR_ARGUMENT, "sequence_starts is NULL but num_sequences > 0");
+    if (args.num_sequences && args.sequence_names)
+        for (uint64_t i = 0; i < args.num_sequences; i++)
+            if (!args.sequence_names[i]) throw Error(SUFR_B200_ERR_ARGUMENT, "sequence_names holds a NULL entry");
     SeedMaskInfo mask;
     const bool has_mask = args.seed_mask && parse_seed_mask(args.seed_mask, mask);
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
                                                            unsigned long long* __restrict__ sample_counts,
                                                            unsigned long long* __restrict__ indexed_count) {
     __shared__ uint32_t seen[256];
-    __shared__ uint32_t cnt[256];  // byte counts of a 1/64 sample (chooses the 4 "regular" bytes)
+    __shared__ uint32_t cnt[256];  // byte counts of a uniform 1/64 sample (chooses the 4 "regular" bytes)
     seen[threadIdx.x] = 0;
     cnt[threadIdx.x] = 0;
     unsigned long long nidx = 0;   // bytes that start an indexed suffix under --dna (sufr_builder.rs:446-449)
@@ -76,8 +76,7 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
     const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const uint64_t nvec = aligned ? n / 16 : 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t iter = 0;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride, iter++) {
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
         uint4 x = reinterpret_cast<const uint4*>(in)[v];
         uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(kBlock) transform_kernel(const uint8_t* __rest
             }
             w[k] = t;
         }
-        if ((iter & 63u) == 0) {  // block-uniform: one grid-stride sweep in 64 is the sample
+        if ((v & 63u) == 0) {  // every 64th 16-byte vector of the text: a uniform 1/64 sample
 #pragma unroll
             for (int k = 0; k < 4; k++)
 #pragma unroll

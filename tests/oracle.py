@@ -213,7 +213,9 @@ class Oracle:
         if k:
             flat = np.ctypeslib.as_array(C.cast(L.oracle_n_ranges(h), C.POINTER(C.c_uint64)), (2 * k,))
             nr = [(int(flat[2 * i]), int(flat[2 * i + 1])) for i in range(k)]
-        fb = C.string_at(L.oracle_file_bytes(h), L.oracle_file_size(h)) if self._sorted else b""
+        # the serialized file only when it is small enough to be useful as a bytes object (ctypes sizes are C ints)
+        fsize = L.oracle_file_size(h) if self._sorted else 0
+        fb = C.string_at(L.oracle_file_bytes(h), fsize) if 0 < fsize < (1 << 30) else b""
         t = (C.c_double * 6)()
         L.oracle_phase_times(h, t)
         keys = ["transform_s", "nscan_s", "pivots_s", "partition_s", "sort_s", "stitch_s"]
