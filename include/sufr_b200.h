@@ -175,6 +175,15 @@ int sufr_b200_write(const SufrB200Args* args, const SufrB200Result* result);
  *    sufr_b200_build / sufr_b200_patch_seam / sufr_b200_write. */
 int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out);
 
+/* -- create on several GPUs of one box in ONE call (sufr::create is one call too, sufr/src/lib.rs:321-371): a host
+ *    thread per device builds key-range shard r of num_devices; the text is uploaded once and replicated over NVLink
+ *    (peer copies), seams are repaired from the shards' (count, first, last), and every device streams its slice of
+ *    the suffix / LCP arrays into args->path at its offset.  index_bits: 32, 64 or 0 = the reference's dispatch
+ *    (suffix_array.rs:460-470).  args->rank / world_size must be 0 / <= 1.  The result is that of sufr_b200_create
+ *    (counts over all shards; timings: the slowest shard).  num_devices == 1 is a plain single-GPU create. */
+int sufr_b200_create_multi(const SufrB200Args* args, const int* devices, int num_devices, uint32_t index_bits,
+                           SufrB200Result* out);
+
 /* -- helpers shared with the host-side mirror ---------------------------------------------- */
 /* SeedMask::new (types.rs:80-97): returns the weight, or -1 if the mask is invalid.
  * bytes/positions/differences may be NULL; otherwise they need strlen(mask) entries. */

@@ -113,7 +113,7 @@ class Sequences(C.Structure):
 ABI_SYMBOLS = [
     "sufr_b200_ctx_create", "sufr_b200_ctx_destroy", "sufr_b200_ctx_reserve", "sufr_b200_ctx_trim",
     "sufr_b200_build", "sufr_b200_result_free", "sufr_b200_patch_seam", "sufr_b200_verify", "sufr_b200_write",
-    "sufr_b200_create",
+    "sufr_b200_create", "sufr_b200_create_multi",
     "sufr_b200_seed_mask", "sufr_b200_find_lcp_full_offset", "sufr_b200_read_sequence_file",
     "sufr_b200_sequences_free", "sufr_b200_synth_dna", "sufr_b200_last_error", "sufr_b200_abi_version",
     "sufr_b200_device_count",
@@ -159,6 +159,8 @@ def lib():
     L.sufr_b200_write.argtypes = [C.POINTER(Args), C.POINTER(Result)]
     L.sufr_b200_create.restype = C.c_int
     L.sufr_b200_create.argtypes = [C.POINTER(Args), C.c_int, C.POINTER(Result)]
+    L.sufr_b200_create_multi.restype = C.c_int
+    L.sufr_b200_create_multi.argtypes = [C.POINTER(Args), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(Result)]
     L.sufr_b200_seed_mask.restype = C.c_int64
     L.sufr_b200_seed_mask.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sufr_b200_find_lcp_full_offset.restype = C.c_uint64

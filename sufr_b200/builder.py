@@ -332,6 +332,22 @@ def build(args: SufrBuilderArgs, *, index_bits: int = 0, ctx: Optional[Context] 
     return BuildResult(ctx, cargs, res)
 
 
+def create_multi(args: SufrBuilderArgs, devices: Sequence[int], index_bits: int = 0) -> dict:
+    """``sufr::create`` on several GPUs of one box in one call (sufr_b200_create_multi): builds and writes
+    ``args.path``; returns the counts and timings of the whole build."""
+    cargs = _CArgs(args)
+    res = _lib.Result()
+    devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+    _check(_lib.lib().sufr_b200_create_multi(C.byref(cargs.c), devs, len(devices), index_bits, C.byref(res)))
+    try:
+        return {"num_suffixes": int(res.num_suffixes), "text_len": int(res.text_len), "index_bits": int(res.index_bits),
+                "timings": res.timings.as_dict(), "kernel_launches": int(res.kernel_launches),
+                "text": C.string_at(res.text, res.text_len) if res.text else b"",
+                "n_ranges": [(int(res.n_ranges[2 * i]), int(res.n_ranges[2 * i + 1])) for i in range(res.num_n_ranges)]}
+    finally:
+        _lib.lib().sufr_b200_result_free(None, C.byref(res))
+
+
 class SufrBuilder:
     """``SufrBuilder::<T>::new(args)``: builds the suffix and LCP arrays on the GPU and writes the
     `.sufr` file at ``args.path`` (default "out.sufr", sufr_builder.rs:215).  ``index_bits`` plays the

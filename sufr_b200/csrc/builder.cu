@@ -15,6 +15,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <condition_variable>
@@ -1165,7 +1166,11 @@ void Build::run(SufrB200Result* out) {
     // widened by host threads while the next copy is in flight: PCIe, not the GPU, bounds the end-to-end time.
     uint64_t compact_min = 1u << 22;
     if (const char* dbg = getenv("SUFR_B200_DEBUG_COMPACT_MIN")) compact_min = strtoull(dbg, nullptr, 10);
+    // Transfer model: one GPU pushes everything through one PCIe link (~50 GB/s), so fewer bytes on the wire win even
+    // though host threads then have to widen them (2 * s * w bytes of stores); from four ranks on, every rank has its own
+    // link and little to send, while the ranks would compete for the same host cores: plain transfer, no widening.
     bool compact = result_memory_ == SUFR_B200_MEM_HOST && s >= compact_min && s > 0 &&
+                   (args.world_size < 4 || getenv("SUFR_B200_DEBUG_COMPACT_MIN")) &&
                    !getenv("SUFR_B200_DEBUG_NO_COMPACT_D2H");
     DevBuf<uint8_t> d_lcp8;
     DevBuf<uint32_t> d_exc_idx, d_exc_val;
@@ -1276,8 +1281,11 @@ void Build::run(SufrB200Result* out) {
         } owner_reset{owner.get()};
         int e1 = timer.mark();
         if (compact) {
+            // the widening is store-bandwidth bound on the host: all cores of this rank's share (one is left for the
+            // thread that feeds the copy engine)
             int hw = (int)std::thread::hardware_concurrency();
-            int threads = std::max(2, std::min(8, hw / (2 * std::max(1, (int)args.world_size))));
+            int threads = std::max(2, std::min(48, hw / std::max(1, (int)args.world_size) - 1));
+            if (const char* dbg = getenv("SUFR_B200_WIDEN_THREADS")) threads = std::max(1, atoi(dbg));
             // 1. LCP bytes + exceptions, widened on the host while the suffix array is in flight
             d2h_bytes_ += s + exc_count * 8 + s * 4 + (want_text ? n : 0);
             uint8_t* h8 = (uint8_t*)ctx.pinned.get(s);
@@ -1563,8 +1571,13 @@ static void stream_result_to_file(Ctx& ctx, const SufrB200Args& args, const Sufr
             if (!text) throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, "out of host memory for the transformed text");
         }
         {
+            // page-cache / tmpfs writes are CPU bound (page allocation + copy, ~1 GB/s per thread): many writers on
+            // many small slots, shared fairly between the ranks of a multi-GPU build
             const int hw = (int)std::thread::hardware_concurrency();
-            StreamWriter sw(fd, path, ctx.device, ctx.stream, 64u << 20, 8, std::max(2, std::min(8, hw / 2)));
+            const int share = std::max(1, (int)args.world_size);
+            int workers = std::max(2, std::min(24, (hw - 2) / share));
+            if (const char* dbg = getenv("SUFR_B200_WRITER_THREADS")) workers = std::max(1, atoi(dbg));
+            StreamWriter sw(fd, path, ctx.device, ctx.stream, 16u << 20, workers + 4, workers);
             if (leader) {
                 pwrite_all(fd, f.head.data(), f.head.size(), 0, path);
                 pwrite_all(fd, f.tail.data(), f.tail.size(), f.names_pos, path);
@@ -1962,6 +1975,176 @@ int sufr_b200_create(const SufrB200Args* args, int device, SufrB200Result* out) 
             throw;
         }
         teardown();
+    });
+    if (rc == SUFR_B200_OK && !out) sufr_b200_result_free(nullptr, &local);
+    return rc;
+}
+
+// One call, several GPUs of one box: a host thread per device builds key-range shard r of `num_devices`, the raw text
+// is uploaded once and replicated over NVLink (peer copies from the first device), the threads exchange
+// (count, first, last) in host memory, every shard repairs its seam LCP and streams its slice of the suffix / LCP
+// arrays into the file at its offset (sufr_builder.rs:817-918 writes the same sections serially).
+int sufr_b200_create_multi(const SufrB200Args* args, const int* devices, int num_devices, uint32_t index_bits,
+                           SufrB200Result* out) {
+    SufrB200Result local;
+    SufrB200Result* res = out ? out : &local;
+    int rc = guarded([&] {
+        if (!args || !devices) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (num_devices < 1 || num_devices > 64) throw Error(SUFR_B200_ERR_ARGUMENT, "num_devices must be 1..64");
+        if (args->world_size > 1)
+            throw Error(SUFR_B200_ERR_ARGUMENT, "sufr_b200_create_multi shards the build itself: pass world_size <= 1");
+        if (args->text_len && !args->text) throw Error(SUFR_B200_ERR_ARGUMENT, "text is NULL");
+        for (int i = 0; i < num_devices; i++)
+            for (int k = 0; k < i; k++)
+                if (devices[i] == devices[k]) throw Error(SUFR_B200_ERR_ARGUMENT, "a device is listed twice");
+        const int W = num_devices;
+        const uint64_t n = args->text_len;
+
+        struct Shard {
+            std::unique_ptr<Ctx> ctx;
+            SufrB200Args a;
+            SufrB200Result dev;
+            uint8_t* host_text = nullptr;
+            double write_ms = 0, h2d_ms = 0;
+            std::exception_ptr err;
+        };
+        std::vector<Shard> sh(W);
+        for (auto& x : sh) memset(&x.dev, 0, sizeof(x.dev));
+        std::atomic<bool> failed{false};
+        struct Barrier {
+            std::mutex mu;
+            std::condition_variable cv;
+            int waiting = 0, generation = 0, parties;
+            explicit Barrier(int p) : parties(p) {}
+            void wait() {
+                std::unique_lock<std::mutex> lock(mu);
+                const int gen = generation;
+                if (++waiting == parties) { waiting = 0; generation++; cv.notify_all(); }
+                else cv.wait(lock, [&] { return gen != generation; });
+            }
+        } bar(W);
+        uint8_t* raw0 = nullptr;  // raw text on the first device
+
+        auto worker = [&](int r) {
+            Shard& me = sh[r];
+            auto step = [&](auto&& f) {
+                if (failed.load()) return;
+                try { f(); } catch (...) { me.err = std::current_exception(); failed.store(true); }
+            };
+            DevBuf<uint8_t> raw;
+            step([&] {
+                me.ctx.reset(make_ctx(devices[r]));
+                me.a = *args;
+                me.a.rank = r;
+                me.a.world_size = W;
+                raw = DevBuf<uint8_t>(me.ctx->pool, n + 16);
+                if (r == 0) {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    if (n) SUFR_CUDA_CHECK(cudaMemcpyAsync(raw.get(), args->text, n, cudaMemcpyHostToDevice, me.ctx->stream));
+                    SUFR_CUDA_CHECK(cudaStreamSynchronize(me.ctx->stream));
+                    me.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                    raw0 = raw.get();
+                } else {
+                    cudaDeviceEnablePeerAccess(devices[0], 0);  // direct NVLink copies when the pair allows it
+                    cudaGetLastError();
+                }
+            });
+            bar.wait();
+            step([&] {
+                if (r > 0 && n) {
+                    SUFR_CUDA_CHECK(cudaMemcpyPeerAsync(raw.get(), devices[r], raw0, devices[0], n, me.ctx->stream));
+                    SUFR_CUDA_CHECK(cudaStreamSynchronize(me.ctx->stream));
+                }
+            });
+            bar.wait();  // the first device keeps its copy alive until every peer has read it
+            step([&] {
+                me.a.text = raw.get();
+                std::lock_guard<std::mutex> lock(me.ctx->mu);
+                Build b(*me.ctx, me.a, index_bits, SUFR_B200_MEM_DEVICE, SUFR_B200_MEM_DEVICE);
+                b.run(&me.dev);
+            });
+            raw.reset();
+            bar.wait();
+            step([&] {
+                // (count, first, last) of every shard are final: offsets, total, previous non-empty shard
+                uint64_t off = 0, total = 0;
+                bool have_prev = false;
+                uint64_t prev_last = 0;
+                for (int k = 0; k < W; k++) {
+                    if (k < r) {
+                        off += sh[k].dev.num_suffixes;
+                        if (sh[k].dev.num_suffixes) { have_prev = true; prev_last = sh[k].dev.last_suffix; }
+                    }
+                    total += sh[k].dev.num_suffixes;
+                }
+                me.dev.shard_offset = off;
+                me.dev.total_suffixes = total;
+                if (have_prev && me.dev.num_suffixes) {
+                    if (sufr_b200_patch_seam(reinterpret_cast<SufrB200Ctx*>(me.ctx.get()), &me.a, &me.dev, prev_last) != SUFR_B200_OK)
+                        throw Error(SUFR_B200_ERR_INTERNAL, "seam repair failed: " + g_last_error);
+                }
+                me.a.text = args->text;  // host text again (unused by the writer)
+                const auto w0 = std::chrono::steady_clock::now();
+                stream_result_to_file(*me.ctx, me.a, me.dev, r == 0 ? &me.host_text : nullptr);
+                me.write_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+            });
+        };
+        std::vector<std::thread> threads;
+        for (int r = 1; r < W; r++) threads.emplace_back(worker, r);
+        worker(0);
+        for (auto& t : threads) t.join();
+
+        // result of the whole build (what SufrBuilder holds after `new`): counts, transformed text, n_ranges
+        auto owner = std::make_unique<ResultOwner>();
+        std::exception_ptr first_err;
+        for (auto& x : sh)
+            if (x.err && !first_err) first_err = x.err;
+        if (!first_err) {
+            owner->memory = SUFR_B200_MEM_HOST;
+            owner->text = sh[0].host_text;
+            owner->text_malloc = true;
+            sh[0].host_text = nullptr;
+            if (sh[0].dev.num_n_ranges) {
+                owner->n_ranges = (uint64_t*)malloc(sh[0].dev.num_n_ranges * 16);
+                memcpy(owner->n_ranges, sh[0].dev.n_ranges, sh[0].dev.num_n_ranges * 16);
+            }
+            *res = sh[0].dev;
+            res->memory = SUFR_B200_MEM_HOST;
+            res->text = (uint8_t*)owner->text;
+            res->sa = nullptr;
+            res->lcp = nullptr;
+            res->n_ranges = owner->n_ranges;
+            res->num_suffixes = sh[0].dev.total_suffixes;
+            res->shard_offset = 0;
+            res->timings.h2d_ms = sh[0].h2d_ms;
+            res->kernel_launches = 0;
+            res->peak_device_bytes = 0;
+            res->d2h_bytes = n;
+            res->h2d_bytes = n;
+            for (auto& x : sh) {
+                res->timings.total_ms = std::max(res->timings.total_ms, x.dev.timings.total_ms);
+                res->timings.d2h_ms = std::max(res->timings.d2h_ms, x.write_ms);
+                res->kernel_launches += x.dev.kernel_launches;
+                res->peak_device_bytes = std::max(res->peak_device_bytes, x.dev.peak_device_bytes);
+                res->d2h_bytes += 2 * x.dev.num_suffixes * (x.dev.index_bits / 8);
+                res->refine_rounds = std::max(res->refine_rounds, x.dev.refine_rounds);
+                res->doubling_rounds = std::max(res->doubling_rounds, x.dev.doubling_rounds);
+            }
+        }
+        for (auto& x : sh) {  // tear the per-device state down on its device
+            if (!x.ctx) continue;
+            cudaSetDevice(x.ctx->device);
+            if (x.dev.owner) free_owner(static_cast<ResultOwner*>(x.dev.owner));
+            x.dev.owner = nullptr;
+            cudaStreamSynchronize(x.ctx->stream);
+            x.ctx->pinned.sizes.clear();
+            x.ctx->pinned.release();
+            x.ctx->pool.release_all();
+            cudaStreamDestroy(x.ctx->stream);
+            free(x.host_text);
+        }
+        if (first_err) std::rethrow_exception(first_err);
+        res->owner = owner.release();
     });
     if (rc == SUFR_B200_OK && !out) sufr_b200_result_free(nullptr, &local);
     return rc;

@@ -29,7 +29,8 @@ struct CreateArgs {  // sufr/src/lib.rs:85-125
     int threads = 0;
     std::string log_level;
     std::string log_file;
-    int device = 0;
+    std::vector<int> devices{0};
+    uint32_t index_bits = 0;  // 0 = the reference's dispatch (u32 below u32::MAX bytes, suffix_array.rs:460-470)
 };
 
 [[noreturn]] void usage_error(const std::string& msg) {
@@ -52,6 +53,8 @@ void print_help() {
          "  -s, --seed-mask <MASK>             Spaced seeds mask\n"
          "  -r, --random-seed <RANDSEED>       Random seed [default: 42]\n"
          "      --device <ORDINAL>             CUDA device [default: 0]\n"
+         "      --devices <LIST>               CUDA devices that share the build, e.g. 0-7 or 0,2,5 (one key-range shard each)\n"
+         "      --index-bits <32|64>           Width of the SA / LCP entries [default: as the reference: 32 below 4 Gi bytes]\n"
          "  -h, --help                         Print help");
 }
 
@@ -70,6 +73,28 @@ std::string file_stem(const std::string& path) {  // PathBuf::file_stem (sufr/sr
     size_t dot = base.find_last_of('.');
     if (dot == std::string::npos || dot == 0) return base;
     return base.substr(0, dot);
+}
+
+std::vector<int> parse_devices(const std::string& flag, const char* v) {  // "0-7", "0,2,5", "3"
+    std::vector<int> out;
+    std::string s = v ? v : "";
+    size_t i = 0;
+    while (i <= s.size()) {
+        size_t j = s.find(',', i);
+        if (j == std::string::npos) j = s.size();
+        std::string part = s.substr(i, j - i);
+        size_t dash = part.find('-');
+        if (part.empty()) usage_error("invalid value '" + s + "' for '" + flag + "'");
+        if (dash == std::string::npos) {
+            out.push_back((int)parse_u64(flag, part.c_str()));
+        } else {
+            int lo = (int)parse_u64(flag, part.substr(0, dash).c_str()), hi = (int)parse_u64(flag, part.substr(dash + 1).c_str());
+            if (hi < lo || hi - lo > 63) usage_error("invalid value '" + s + "' for '" + flag + "'");
+            for (int d = lo; d <= hi; d++) out.push_back(d);
+        }
+        i = j + 1;
+    }
+    return out;
 }
 
 double now_s() {
@@ -108,7 +133,12 @@ int main(int argc, char** argv) {
         }
         else if (key == "-s" || key == "--seed-mask") { a.seed_mask = value(key); a.has_mask = true; }
         else if (key == "-r" || key == "--random-seed") a.random_seed = parse_u64(key, value(key));
-        else if (key == "--device") a.device = (int)parse_u64(key, value(key));
+        else if (key == "--device") a.devices = {(int)parse_u64(key, value(key))};
+        else if (key == "--devices") a.devices = parse_devices(key, value(key));
+        else if (key == "--index-bits") {
+            a.index_bits = (uint32_t)parse_u64(key, value(key));
+            if (a.index_bits != 32 && a.index_bits != 64) usage_error("invalid value for '--index-bits <32|64>'");
+        }
         else if (!s.empty() && s[0] == '-' && s.size() > 1) usage_error("unexpected argument '" + s + "' found");
         else if (!saw_create && (s == "create" || s == "cr")) saw_create = true;
         else pos.push_back(s);
@@ -161,7 +191,9 @@ int main(int argc, char** argv) {
 
     t0 = now_s();
     SufrB200Result res;
-    int rc = sufr_b200_create(&args, a.device, &res);
+    int rc = (a.devices.size() == 1 && a.index_bits == 0)
+                 ? sufr_b200_create(&args, a.devices[0], &res)
+                 : sufr_b200_create_multi(&args, a.devices.data(), (int)a.devices.size(), a.index_bits, &res);
     if (rc != SUFR_B200_OK) {
         fprintf(stderr, "Error: %s\n", sufr_b200_last_error());  // sufr/src/main.rs:9-12
         sufr_b200_sequences_free(&seqs);
@@ -171,9 +203,9 @@ int main(int argc, char** argv) {
         const SufrB200Timings& t = res.timings;
         fprintf(logf, "Encoded text (alphabet %u, %u bits/symbol) in %.3fms\n", res.alphabet_size, res.bits_per_symbol,
                 t.encode_ms);
-        fprintf(logf, "Sorted %llu suffixes on the GPU in %.3fms (keys %.3f, sort %.3f, refine %.3f [%u word / %u doubling rounds], "
+        fprintf(logf, "Sorted %llu suffixes on %zu GPU%s in %.3fms (keys %.3f, sort %.3f, refine %.3f [%u word / %u doubling rounds], "
                       "lcp %.3f, finish %.3f; h2d %.3f, d2h %.3f; %llu kernel launches)\n",
-                (unsigned long long)res.num_suffixes, t.total_ms, t.keys_ms, t.sort_ms, t.refine_ms, res.refine_rounds,
+                (unsigned long long)res.num_suffixes, a.devices.size(), a.devices.size() == 1 ? "" : "s", t.total_ms, t.keys_ms, t.sort_ms, t.refine_ms, res.refine_rounds,
                 res.doubling_rounds, t.lcp_ms, t.finish_ms, t.h2d_ms, t.d2h_ms, (unsigned long long)res.kernel_launches);
         struct stat sb;
         unsigned long long bytes = stat(outfile.c_str(), &sb) == 0 ? (unsigned long long)sb.st_size : 0;

@@ -268,6 +268,53 @@ def test_key_range_shards_concatenate(S, world, kw):
     assert sum(1 for s in shards if s.num_suffixes) >= min(world, 2)
 
 
+@pytest.mark.parametrize("world", [4, 16, 64])
+@pytest.mark.parametrize("general_path", [False, True], ids=["fast2", "3bit"])
+def test_shards_keep_n_run_tie_chains_together(S, monkeypatch, world, general_path):
+    """N-run tie rule (sufr_builder.rs:305-307, :701-712) under sharding: many recorded runs (>= 1000 N) that end in
+    the same base make long chains of equal (remaining run length, next byte) -- suffixes N^r A.. with r = 1..3 fall
+    into different 12-bit histogram bins, so a key-range cut between the 'NA??' bins would split a chain and the
+    concatenated shards would differ from the unsharded (and the reference's) order.  With many shards the cuts land
+    everywhere; no cut may fall inside the N-prefixed key range."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    if general_path:
+        monkeypatch.setenv("SUFR_B200_DEBUG_NO_FAST2", "1")
+    rng = np.random.default_rng(world)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    parts = []
+    for k in range(40):
+        parts.append(acgt[rng.integers(0, 4, int(rng.integers(20, 200)))])
+        parts.append(np.full(1000 + (k % 3), ord("N"), dtype=np.uint8))  # runs of 1000..1002 N
+        parts.append(np.frombuffer(b"A", dtype=np.uint8))                 # all followed by the same base
+        parts.append(acgt[rng.integers(0, 4, 3)])                          # and then different continuations
+    text = np.concatenate(parts).tobytes() + b"$"
+    kw = dict(is_dna=True, allow_ambiguity=True)
+    want = O.oracle_build(text, num_partitions=16, threads=4, **kw)
+    assert len(want.n_ranges) == 40
+    shards = [S.build(S.SufrBuilderArgs(text=text, **kw), rank=r, world_size=world) for r in range(world)]
+    try:
+        meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+        offs, total = shard_layout(meta)
+        assert total == want.num_suffixes
+        for r, s in enumerate(shards):
+            s.set_shard_layout(offs[r], total)
+            prev = previous_last_suffix(meta, r)
+            if prev is not None and s.num_suffixes:
+                s.patch_seam(prev)
+        sa = np.concatenate([s.sa for s in shards])
+        lcp = np.concatenate([s.lcp for s in shards])
+        assert np.array_equal(sa, want.sa)
+        assert np.array_equal(lcp, want.lcp)
+    finally:
+        for s in shards:
+            s.free()
+
+
+def test_sequence_names_must_match_starts(S):
+    with pytest.raises(S.SufrError, match="sequence_names has 1 entries but sequence_starts has 2"):
+        S.build(S.SufrBuilderArgs(text=b"ACGT%ACGT$", sequence_starts=[0, 5], sequence_names=["a"]))
+
+
 def test_device_resident_result_and_text(S):
     """The bench's device-resident path: text already in HBM, SA/LCP left in HBM."""
     import torch

@@ -219,3 +219,41 @@ def test_config5_100m_fully_verified(S):
         assert rep["pairs_checked"] == r.num_suffixes - 1 and rep["method"] == 2 and rep["max_lcp"] > 100_000
     finally:
         r.free()
+
+
+# ------------------------------------------------------------------ one call, several GPUs (sufr_b200_create_multi)
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("kw,bits", [(dict(is_dna=True), 64), (dict(is_dna=True, allow_ambiguity=True), 32),
+                                     (dict(is_dna=True, seed_mask="1101101101"), 32), (dict(), 32)],
+                         ids=["dna_u64", "dna_amb", "mask", "protein"])
+def test_create_multi_file_is_byte_identical(S, tmp_path, kw, bits):
+    """sufr_b200_create_multi over every visible GPU (a single-GPU box degenerates to one shard): the file is
+    byte-identical to the oracle's."""
+    ndev = max(1, min(8, _ngpus()))
+    alphabet = b"ACGTN%" if kw.get("is_dna") else b"ACDEFGHIKLMNPQRSTVWY%"
+    text = rand_dna(77, 400_000, repeat_p=0.01, alphabet=alphabet)
+    starts, names = [0, 1000], ["chrA", "chrB"]
+    want = O.oracle_build(text, num_partitions=16, threads=4, index_bits=bits, sequence_starts=starts,
+                          sequence_names=names, **kw)
+    out = tmp_path / "multi.sufr"
+    info = S.create_multi(S.SufrBuilderArgs(text=text, path=str(out), sequence_starts=starts, sequence_names=names, **kw),
+                          list(range(ndev)), index_bits=bits)
+    assert info["num_suffixes"] == want.num_suffixes and info["text"] == want.text
+    assert out.read_bytes() == want.file_bytes
+
+
+def test_cli_devices_flag(S, tmp_path):
+    import subprocess
+    from conftest import GOLDEN, ROOT
+    ndev = max(1, min(8, _ngpus()))
+    out = tmp_path / "cli.sufr"
+    devs = "0" if ndev == 1 else f"0-{ndev - 1}"
+    p = subprocess.run([str(ROOT / "sufr_b200" / "sufr-b200"), "create", "--dna", "--devices", devs, "--log", "info",
+                        "-o", str(out), str(GOLDEN / "inputs" / "long_dna_sequence.fa")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert out.read_bytes() == (GOLDEN / "expected" / "long_dna_sequence.sufr").read_bytes()
+    assert f"on {ndev} GPU" in p.stdout

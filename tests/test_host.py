@@ -43,7 +43,8 @@ def test_struct_layouts_match_header(S):
     #include <stdio.h>
     #include <stddef.h>
     int main(void) {
-      printf("%zu %zu %zu %zu\n", sizeof(SufrB200Args), sizeof(SufrB200Result), sizeof(SufrB200Timings), sizeof(SufrB200Sequences));
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(SufrB200Args), sizeof(SufrB200Result), sizeof(SufrB200Timings),
+             sizeof(SufrB200Sequences), sizeof(SufrB200VerifyReport), offsetof(SufrB200VerifyReport, ms));
       printf("%zu %zu %zu %zu %zu\n", offsetof(SufrB200Args, max_query_len), offsetof(SufrB200Args, seed_mask),
              offsetof(SufrB200Args, rank), offsetof(SufrB200Result, timings), offsetof(SufrB200Result, owner));
       return 0; }'''
@@ -52,7 +53,8 @@ def test_struct_layouts_match_header(S):
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", str(ROOT / "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")], text=True).split()
-    sizes = [C.sizeof(_lib.Args), C.sizeof(_lib.Result), C.sizeof(_lib.Timings), C.sizeof(_lib.Sequences)]
+    sizes = [C.sizeof(_lib.Args), C.sizeof(_lib.Result), C.sizeof(_lib.Timings), C.sizeof(_lib.Sequences),
+             C.sizeof(_lib.VerifyReport), _lib.VerifyReport.ms.offset]
     offs = [_lib.Args.max_query_len.offset, _lib.Args.seed_mask.offset, _lib.Args.rank.offset,
             _lib.Result.timings.offset, _lib.Result.owner.offset]
     assert [int(x) for x in out] == sizes + offs
