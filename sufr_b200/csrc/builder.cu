@@ -224,6 +224,7 @@ class Build {
     uint32_t alphabet = 0;
     uint32_t code_n_ = 0;  // packed-text code of 'N' (0 = the text has none)
     uint32_t refine_rounds = 0, doubling_rounds = 0;
+    uint64_t doubling_depth_ = 0;  // h of the last prefix-doubling round
 
     DevBuf<uint8_t> d_text;     // transformed text
     DevBuf<uint64_t> d_words;   // packed text
@@ -312,6 +313,8 @@ class Build {
     void n_run_rule();
     void apply_filter();
     void segmented_sort_u64key(DevBuf<uint64_t>& ck, DevBuf<uint32_t>& pos, uint64_t m, int key_bits);
+    void sort_groups(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& pos, const uint32_t* seg, const uint32_t* slot, uint64_t m,
+                     uint64_t nseg, int key_lo, int key_hi, bool rank_keys);
 };
 
 static int bits_for(uint64_t v) {  // number of bits needed to represent values 0..v
@@ -692,6 +695,70 @@ void Build::segmented_sort_u64key(DevBuf<uint64_t>& ck, DevBuf<uint32_t>& pos, u
     }
 }
 
+// Sorts every unresolved group by key bits [key_lo, key_hi) of its members' keys (keys, positions, SA slots).
+// rank_keys: prefix-doubling keys (group << 32 | rank); else key words.
+void Build::sort_groups(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& pos, const uint32_t* seg, const uint32_t* slot, uint64_t m,
+                        uint64_t nseg, int key_lo, int key_hi, bool rank_keys) {
+    auto is_large = dalloc<uint8_t>(nseg ? nseg : 1);
+    auto d_any = dalloc<unsigned long long>(1);
+    SUFR_CUDA_CHECK(cudaMemsetAsync(is_large.get(), 0, nseg ? nseg : 1, st()));
+    SUFR_CUDA_CHECK(cudaMemsetAsync(d_any.get(), 0, 8, st()));
+    // small groups: sorted in registers by the thread at the group start
+    small_groups_kernel<<<grid_for(m, 1), kBlock, 0, st()>>>(m, seg, slot, pos.get(), keys.get(), d_sa.get(), is_large.get(),
+                                                            d_any.get());
+    SUFR_KERNEL_CHECK();
+    launched();
+    unsigned long long any_large = 0;
+    SUFR_CUDA_CHECK(cudaMemcpyAsync(&any_large, d_any.get(), 8, cudaMemcpyDeviceToHost, st()));
+    SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+    if (!any_large) return;
+    // larger groups: stable radix sort by (group, key): LSD, the key bits first, then the group bits
+    DevBuf<unsigned long long> part;
+    LargeIn lin{seg, is_large.get()};
+    const unsigned long long lt = scan_begin(m, lin, scan::SumU64{}, part);
+    const uint64_t ml = (uint32_t)lt, nlseg = lt >> 32;
+    if (ml == 0) return;
+    if (rank_keys && ml * 4 > m) {
+        // most of the round sits in large groups (tandem repeats): sort everything in place of a compaction -- the lean
+        // path, 12 bytes of temporary per element; the small groups are simply sorted again
+        part.reset();
+        segmented_sort_u64key(keys, pos, m, key_hi + (nseg > 1 ? bits_for(nseg - 1) : 0));
+        writeback_pos_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, pos.get(), slot, d_sa.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        return;
+    }
+    const int sb = nlseg > 1 ? bits_for(nlseg - 1) : 0;
+    auto idx = dalloc<uint32_t>(ml);
+    if (rank_keys) {
+        auto lck = dalloc<uint64_t>(ml), lck_b = dalloc<uint64_t>(ml);
+        auto lpos = dalloc<uint32_t>(ml), lpos_b = dalloc<uint32_t>(ml);
+        scan_finish(m, lin, scan::SumU64{}, LargeOutRank{pos.get(), keys.get(), idx.get(), lck.get(), lpos.get(), key_hi}, part);
+        // (compact group << rank bits | rank): one sort over rank and group bits together
+        bool in_b = rsort::sort_pairs<uint64_t, uint32_t>(lck.get(), lck_b.get(), lpos.get(), lpos_b.get(), ml, key_lo,
+                                                          key_hi + sb, d_counts.get(), st(), &ctx.launches);
+        if (in_b) { std::swap(lck, lck_b); std::swap(lpos, lpos_b); }
+        scatter_large_rank_kernel<<<grid_for(ml, 2), kBlock, 0, st()>>>(ml, lck.get(), lpos.get(), idx.get(), slot, keys.get(),
+                                                                       pos.get(), d_sa.get(), key_hi);
+    } else {
+        auto lkeys = dalloc<uint64_t>(ml), keys_b = dalloc<uint64_t>(ml);
+        auto segpos = dalloc<uint64_t>(ml), segpos_b = dalloc<uint64_t>(ml);
+        scan_finish(m, lin, scan::SumU64{}, LargeOut{pos.get(), keys.get(), idx.get(), lkeys.get(), segpos.get()}, part);
+        bool in_b = rsort::sort_pairs<uint64_t, uint64_t>(lkeys.get(), keys_b.get(), segpos.get(), segpos_b.get(), ml, key_lo,
+                                                          key_hi, d_counts.get(), st(), &ctx.launches);
+        if (in_b) { std::swap(lkeys, keys_b); std::swap(segpos, segpos_b); }
+        if (sb) {
+            in_b = rsort::sort_pairs<uint64_t, uint64_t>(segpos.get(), segpos_b.get(), lkeys.get(), keys_b.get(), ml, 32, 32 + sb,
+                                                         d_counts.get(), st(), &ctx.launches);
+            if (in_b) { std::swap(lkeys, keys_b); std::swap(segpos, segpos_b); }
+        }
+        scatter_large_kernel<<<grid_for(ml, 2), kBlock, 0, st()>>>(ml, lkeys.get(), segpos.get(), idx.get(), slot, keys.get(),
+                                                                  pos.get(), d_sa.get());
+    }
+    SUFR_KERNEL_CHECK();
+    launched();
+}
+
 void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     const uint32_t K = ks.pt.K;
     const int used = (int)(K * ks.pt.bits);
@@ -826,54 +893,18 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         }
         word++;
         refine_rounds++;
+        if (getenv("SUFR_B200_LOG_ROUNDS")) {
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            fprintf(stderr, "[sufr_b200] word round %u (key word %d): unresolved = %llu in %llu groups, t = %.3f s\n",
+                    refine_rounds, word, (unsigned long long)m, (unsigned long long)nseg,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count());
+        }
         final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
         auto keys = dalloc<uint64_t>(m);
-        {
-            // small groups: sorted in registers by the thread at the group start
-            auto is_large = dalloc<uint8_t>(nseg ? nseg : 1);
-            auto d_large = dalloc<unsigned long long>(1);
-            SUFR_CUDA_CHECK(cudaMemsetAsync(is_large.get(), 0, nseg ? nseg : 1, st()));
-            SUFR_CUDA_CHECK(cudaMemsetAsync(d_large.get(), 0, 8, st()));
-            small_segments_kernel<<<grid_for(m, 1), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, seg.get(),
-                                                                      slot.get(), pos.get(), keys.get(), d_sa.get(),
-                                                                      is_large.get(), d_large.get());
-            SUFR_KERNEL_CHECK();
-            launched();
-            unsigned long long any_large = 0;
-            SUFR_CUDA_CHECK(cudaMemcpyAsync(&any_large, d_large.get(), 8, cudaMemcpyDeviceToHost, st()));
-            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
-            if (any_large) {
-                // large groups: stable sort by (group, key word): LSD, key word first, then the group bits
-                auto idx = dalloc<uint32_t>(m);
-                auto lpos = dalloc<uint32_t>(m);
-                auto lseg = dalloc<uint32_t>(m);
-                unsigned long long lt = scan_total(m, LargeIn{seg.get(), is_large.get()}, scan::SumU64{},
-                                                   LargeOut{pos.get(), idx.get(), lpos.get(), lseg.get()});
-                const uint64_t ml = (uint32_t)lt;
-                const uint64_t nlseg = lt >> 32;
-                auto lkeys = dalloc<uint64_t>(ml);
-                auto segpos = dalloc<uint64_t>(ml);
-                active_keys_kernel<<<grid_for(ml, 2), kBlock, 0, st()>>>(ks, ml, (uint32_t)word, sentinel_ ? 1 : 0,
-                                                                        lpos.get(), lseg.get(), lkeys.get(), segpos.get());
-                SUFR_KERNEL_CHECK();
-                launched();
-                auto keys_b = dalloc<uint64_t>(ml);
-                auto segpos_b = dalloc<uint64_t>(ml);
-                bool in_b = rsort::sort_pairs<uint64_t, uint64_t>(lkeys.get(), keys_b.get(), segpos.get(), segpos_b.get(), ml,
-                                                                  64 - used, 64, d_counts.get(), st(), &ctx.launches);
-                if (in_b) { std::swap(lkeys, keys_b); std::swap(segpos, segpos_b); }
-                if (nlseg > 1) {
-                    int sb = bits_for(nlseg - 1);
-                    in_b = rsort::sort_pairs<uint64_t, uint64_t>(segpos.get(), segpos_b.get(), lkeys.get(), keys_b.get(), ml,
-                                                                 32, 32 + sb, d_counts.get(), st(), &ctx.launches);
-                    if (in_b) { std::swap(lkeys, keys_b); std::swap(segpos, segpos_b); }
-                }
-                scatter_large_kernel<<<grid_for(ml, 2), kBlock, 0, st()>>>(ml, lkeys.get(), segpos.get(), idx.get(),
-                                                                          slot.get(), keys.get(), pos.get(), d_sa.get());
-                SUFR_KERNEL_CHECK();
-                launched();
-            }
-        }
+        round_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, pos.get(), keys.get());
+        SUFR_KERNEL_CHECK();
+        launched();
+        sort_groups(keys, pos, seg.get(), slot.get(), m, nseg, 64 - used, 64, false);
         ViewActive va{keys.get(), pos.get(), seg.get(), slot.get()};
         resolve_kernel<ViewActive><<<grid_for(m, 2), kBlock, 0, st()>>>(va, m, ks, (uint32_t)word, final_word, 0,
                                                                        d_lcp.get());
@@ -908,20 +939,27 @@ void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<uint32_t>& pos, DevBuf<uint3
     SUFR_KERNEL_CHECK();
     launched();
     scan_total(m, GroupStartIn{seg.get()}, scan::MaxU32{}, GroupRankOut{slot.get(), pos.get(), isa_ptr});
+    const bool log_rounds = getenv("SUFR_B200_LOG_ROUNDS") != nullptr;
     while (m > 0) {
         if (doubling_rounds > 64) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling did not converge");
         doubling_rounds++;
+        doubling_depth_ = h;
+        if (log_rounds) {
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            fprintf(stderr, "[sufr_b200] doubling round %u: h = %llu, unresolved = %llu in %llu groups, t = %.3f s\n",
+                    doubling_rounds, (unsigned long long)h, (unsigned long long)m, (unsigned long long)nseg,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count());
+        }
         auto ck = dalloc<uint64_t>(m);
-        doubling_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, n, h, pos.get(), seg.get(), isa_ptr, ck.get());
+        const int rank_bits = bits_for(n);  // ranks are 0 .. n
+        doubling_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, n, h, pos.get(), seg.get(), isa_ptr, ck.get(), rank_bits);
         SUFR_KERNEL_CHECK();
         launched();
-        segmented_sort_u64key(ck, pos, m, 32 + (nseg > 1 ? bits_for(nseg - 1) : 0));
-        writeback_pos_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(m, pos.get(), slot.get(), d_sa.get());
-        SUFR_KERNEL_CHECK();
-        launched();
+        // the group number sits in the high half of every key and is equal inside a group: sort on the rank bits
+        sort_groups(ck, pos, seg.get(), slot.get(), m, nseg, 0, rank_bits, true);
         uint32_t mark = kLcpLowerBound | (uint32_t)(h < 0x7FFFFFFFull ? h : 0x7FFFFFFFull);
         scan_total(m, DoublingStartIn{ck.get()}, scan::MaxU32{},
-                   DoublingRankOut{ck.get(), slot.get(), pos.get(), isa_ptr, d_lcp.get(), mark});
+                   DoublingRankOut{ck.get(), slot.get(), pos.get(), isa_ptr, d_lcp.get(), mark, rank_bits});
         DevBuf<unsigned long long> part;
         DoublingActiveIn din{ck.get(), m};
         unsigned long long tot = scan_begin(m, din, scan::SumU64{}, part);
@@ -1102,6 +1140,7 @@ void Build::run(SufrB200Result* out) {
         keys_spare_.reset();
         pos_spare_.reset();
         refine_rounds = doubling_rounds = 0;
+        doubling_depth_ = 0;
         for (auto& ev : downsweep_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
         downsweep_events.clear();
         sliced = sharded;
@@ -1117,8 +1156,13 @@ void Build::run(SufrB200Result* out) {
     if (doubling_rounds || (filter_active && !prefilter) || sliced) drop_wide();
     if (doubling_rounds && s) {
         if (!d_isa || s != n) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling ran on a partial suffix set");
-        uint64_t chunks = div_up(n, kPlcpChunk);
-        plcp_complete_kernel<<<grid_for(chunks, 1), kBlock, 0, st()>>>(ks, n, d_sa.get(), d_isa.get(), d_lcp.get());
+        if (doubling_depth_ <= 8192 && !getenv("SUFR_B200_DEBUG_PLCP")) {
+            // shallow repeats: extend every marked pair from its lower bound (at most 2h symbols each)
+            lcp_bounds_direct_kernel<<<grid_for(s, 4), kBlock, 0, st()>>>(ks, s, d_sa.get(), d_lcp.get());
+        } else {
+            uint64_t chunks = div_up(n, kPlcpChunk);
+            plcp_complete_kernel<<<grid_for(chunks, 1), kBlock, 0, st()>>>(ks, n, d_sa.get(), d_isa.get(), d_lcp.get());
+        }
         SUFR_KERNEL_CHECK();
         launched();
     }
@@ -1280,6 +1324,9 @@ void Build::run(SufrB200Result* out) {
             ~OwnerReset() { if (!keep) { o->text = o->sa = o->lcp = nullptr; } }
         } owner_reset{owner.get()};
         int e1 = timer.mark();
+        const bool log_e2e = getenv("SUFR_B200_LOG_E2E") != nullptr;
+        const auto wall0 = std::chrono::steady_clock::now();
+        auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
         if (compact) {
             // the widening is store-bandwidth bound on the host: all cores of this rank's share (one is left for the
             // thread that feeds the copy engine)
@@ -1297,6 +1344,7 @@ void Build::run(SufrB200Result* out) {
                 SUFR_CUDA_CHECK(cudaMemcpyAsync(eval.data(), d_exc_val.get(), exc_count * 4, cudaMemcpyDeviceToHost, st()));
             }
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            if (log_e2e) fprintf(stderr, "[sufr_b200] e2e: LCP bytes on the host after %.1f ms (%d widening threads)\n", since(), threads);
             void* lcp_out = owner->lcp;
             const uint32_t bits = index_bits_;
             std::thread lcp_worker([=, &eidx, &eval]() {
@@ -1314,6 +1362,7 @@ void Build::run(SufrB200Result* out) {
                     });
                 }
                 for (auto& th : pool) th.join();
+                if (log_e2e) fprintf(stderr, "[sufr_b200] e2e: LCP widened after %.1f ms\n", since());
             });
             struct Joiner {  // a CUDA error below must not leave the worker running on freed buffers
                 std::thread& t;
@@ -1343,7 +1392,9 @@ void Build::run(SufrB200Result* out) {
                 SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->sa, d_sa.get(), s * 4, cudaMemcpyDeviceToHost, st()));
             }
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            if (log_e2e) fprintf(stderr, "[sufr_b200] e2e: text + SA transferred and widened after %.1f ms\n", since());
             lcp_worker.join();
+            if (log_e2e) fprintf(stderr, "[sufr_b200] e2e: done after %.1f ms\n", since());
         } else {
             d2h_bytes_ += 2 * s * w + (want_text ? n : 0);
             if (n && want_text) SUFR_CUDA_CHECK(cudaMemcpyAsync(owner->text, d_text.get(), n, cudaMemcpyDeviceToHost, st()));

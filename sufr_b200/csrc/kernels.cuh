@@ -1067,6 +1067,37 @@ struct LcpActiveOut {
     }
 };
 
+// Boundaries created by prefix doubling carry a lower bound (kLcpLowerBound | h, true LCP in [h, 2h)).  While the
+// doubling stayed shallow the exact values are cheapest by extending each marked pair from its bound; deep repeats
+// take the text-order walk of plcp_complete_kernel instead (O(n + chunks * LCP) rather than O(sum of LCP)).
+__global__ void __launch_bounds__(kBlock) lcp_bounds_direct_kernel(KeySpec ks, uint64_t s, const uint32_t* __restrict__ sa,
+                                                                   uint32_t* __restrict__ lcp) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < s; j0 += stride) {
+        uint32_t v[4];
+        if (j0 + 3 < s) {
+            uint4 x = *reinterpret_cast<const uint4*>(lcp + j0);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = j0 + u < s ? lcp[j0 + u] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t j = j0 + u;
+            if (j == 0 || j >= s || v[u] >= kLcpFixup || !(v[u] & kLcpLowerBound)) continue;
+            const uint64_t pa = sa[j - 1], pb = sa[j];
+            uint64_t ea, eb;
+            if (ks.num_n_ranges && n_run_end(ks, pa, ea) && n_run_end(ks, pb, eb)) {
+                const uint64_t ra = ea - pa, rb = eb - pb;
+                lcp[j] = (uint32_t)(ra < rb ? ra : rb);  // sufr_builder.rs:305-307
+            } else {
+                lcp[j] = (uint32_t)lcp_direct(ks, pa, pb, v[u] & ~kLcpLowerBound);
+            }
+        }
+    }
+}
+
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
 // previous SA slot's key
 struct SparseSegIn {
@@ -1116,31 +1147,31 @@ struct ActiveOut {
     }
 };
 
-// Next key word of every active element, packed with (segment, position) as the sort payload.
-__global__ void __launch_bounds__(kBlock) active_keys_kernel(KeySpec ks, uint64_t m, uint32_t word, int filter,
-                                                             const uint32_t* __restrict__ pos,
-                                                             const uint32_t* __restrict__ seg,
-                                                             uint64_t* __restrict__ keys,
-                                                             uint64_t* __restrict__ segpos) {
+// ---- one refinement round = sort every unresolved group by a 64-bit key of its members
+// (word rounds: the next key word; prefix doubling: group << 32 | rank of the suffix h symbols further on).
+//   round_keys_kernel        the keys of ALL unresolved elements, one thread per element (independent gathers)
+//   small_groups_kernel      groups of at most kSmallSeg members: the thread at the group start rank-sorts them in
+//                            registers (stable) and writes keys, positions and SA slots in place.  On repetitive
+//                            texts most unresolved groups are pairs (a segment and its copy).
+//   LargeIn / LargeOut*      the members of the larger groups, compacted for the radix sort;
+//   scatter_large*_kernel    and put back.
+// (Measured and dropped: skipping large groups whose members are already in order.  The groups of a tandem-repeat
+// text -- ~10^3..10^4 suffixes each, unresolved for log2(LCP) doubling rounds -- mix the arrays that share a unit, and
+// do get re-ordered in almost every round: profiles/r2_round_log_config5.txt.)
+constexpr int kSmallSeg = 8;
+__global__ void __launch_bounds__(kBlock) round_keys_kernel(KeySpec ks, uint64_t m, uint32_t word, int filter,
+                                                            const uint32_t* __restrict__ pos, uint64_t* __restrict__ keys) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
-        uint32_t p = pos[a];
+        const uint32_t p = pos[a];
         keys[a] = (filter && !indexed_byte(ks.text[p])) ? ~0ull : key_word(ks, p, word);
-        segpos[a] = ((uint64_t)seg[a] << 32) | p;
     }
 }
-
-// Refinement of SMALL groups without a global sort.  On repetitive texts most unresolved groups are pairs
-// (a segment and its copy); the thread at the start of a group of at most kSmallSeg elements loads their
-// next key words, rank-sorts them in registers (stable) and writes keys, positions and SA slots in place.
-// Larger groups are flagged and go through the segmented radix sort.
-constexpr int kSmallSeg = 8;
-__global__ void __launch_bounds__(kBlock) small_segments_kernel(KeySpec ks, uint64_t m, uint32_t word, int filter,
-                                                                const uint32_t* __restrict__ seg,
-                                                                const uint32_t* __restrict__ slot,
-                                                                uint32_t* __restrict__ pos, uint64_t* __restrict__ keys,
-                                                                uint32_t* __restrict__ sa, uint8_t* __restrict__ is_large,
-                                                                unsigned long long* __restrict__ large_elems) {
+__global__ void __launch_bounds__(kBlock) small_groups_kernel(uint64_t m, const uint32_t* __restrict__ seg,
+                                                              const uint32_t* __restrict__ slot, uint32_t* __restrict__ pos,
+                                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ sa,
+                                                              uint8_t* __restrict__ is_large,
+                                                              unsigned long long* __restrict__ any_large) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
         const uint32_t g = seg[a];
@@ -1149,21 +1180,24 @@ __global__ void __launch_bounds__(kBlock) small_segments_kernel(KeySpec ks, uint
         while (len <= kSmallSeg && a + len < m && seg[a + len] == g) len++;
         if (len > kSmallSeg) {
             is_large[g] = 1;
-            *large_elems = 1;  // "some group is large" (benign race: every writer stores 1)
+            *any_large = 1;  // "some group is large" (benign race: every writer stores 1)
             continue;
         }
         uint32_t p[kSmallSeg];
         uint64_t k[kSmallSeg];
+        bool sorted = true;
 #pragma unroll
         for (int i = 0; i < kSmallSeg; i++) {
             if (i < len) {
                 p[i] = pos[a + i];
-                k[i] = (filter && !indexed_byte(ks.text[p[i]])) ? ~0ull : key_word(ks, p[i], word);
+                k[i] = keys[a + i];
+                if (i > 0 && k[i] < k[i - 1]) sorted = false;
             } else {
                 p[i] = 0;
                 k[i] = ~0ull;
             }
         }
+        if (sorted) continue;  // already in order: nothing to write
 #pragma unroll
         for (int i = 0; i < kSmallSeg; i++) {
             if (i < len) {
@@ -1178,31 +1212,65 @@ __global__ void __launch_bounds__(kBlock) small_segments_kernel(KeySpec ks, uint
         }
     }
 }
-// elements of the large groups, in order
+// elements of the flagged groups, in order
 struct LargeIn {
     const uint32_t* seg;
-    const uint8_t* is_large;
+    const uint8_t* flagged;
     __device__ unsigned long long operator()(uint64_t a) const {
         uint32_t g = seg[a];
-        if (!is_large[g]) return 0ull;
+        if (!flagged[g]) return 0ull;
         bool head = a == 0 || seg[a - 1] != g;
         return 1ull | ((unsigned long long)head << 32);
     }
 };
 struct LargeOut {
     const uint32_t* pos;
+    const uint64_t* keys;
     uint32_t* idx;      // index in the active arrays
-    uint32_t* lpos;
-    uint32_t* lseg;
+    uint64_t* lkeys;
+    uint64_t* segpos;   // compact group number << 32 | position
     __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
         if (val & 1ull) {
             uint32_t b = (uint32_t)incl - 1;
             idx[b] = (uint32_t)a;
-            lpos[b] = pos[a];
-            lseg[b] = (uint32_t)(incl >> 32) - 1;
+            lkeys[b] = keys[a];
+            segpos[b] = (((incl >> 32) - 1) << 32) | pos[a];
         }
     }
 };
+// prefix doubling: composite key (compact group number << rank_bits | rank), the position as the payload
+struct LargeOutRank {
+    const uint32_t* pos;
+    const uint64_t* keys;
+    uint32_t* idx;
+    uint64_t* lck;
+    uint32_t* lpos;
+    int rank_bits;
+    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            uint32_t b = (uint32_t)incl - 1;
+            idx[b] = (uint32_t)a;
+            lck[b] = (((incl >> 32) - 1) << rank_bits) | (keys[a] & ((1ull << rank_bits) - 1ull));
+            lpos[b] = pos[a];
+        }
+    }
+};
+__global__ void __launch_bounds__(kBlock) scatter_large_rank_kernel(uint64_t ml, const uint64_t* __restrict__ lck,
+                                                                    const uint32_t* __restrict__ lpos,
+                                                                    const uint32_t* __restrict__ idx,
+                                                                    const uint32_t* __restrict__ slot,
+                                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ pos,
+                                                                    uint32_t* __restrict__ sa, int rank_bits) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rmask = (1ull << rank_bits) - 1ull;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < ml; b += stride) {
+        const uint32_t a = idx[b];
+        const uint32_t p = lpos[b];
+        keys[a] = (keys[a] & ~rmask) | (lck[b] & rmask);  // the group number stays
+        pos[a] = p;
+        sa[slot[a]] = p;
+    }
+}
 __global__ void __launch_bounds__(kBlock) scatter_large_kernel(uint64_t ml, const uint64_t* __restrict__ lkeys,
                                                                const uint64_t* __restrict__ lsegpos,
                                                                const uint32_t* __restrict__ idx,
@@ -1257,17 +1325,18 @@ struct GroupRankOut {
     __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const { isa[pos[a]] = slot[first]; }
 };
 
-// composite key (segment << 32 | rank of suffix p+h, 0 = beyond the end)
+// composite key (segment << rank_bits | rank of suffix p+h, 0 = beyond the end); rank_bits = bits of n, so that
+// the radix sort of a round covers as few digits as possible
 __global__ void __launch_bounds__(kBlock) doubling_keys_kernel(uint64_t m, uint64_t n, uint64_t h,
                                                                const uint32_t* __restrict__ pos,
                                                                const uint32_t* __restrict__ seg,
                                                                const uint32_t* __restrict__ isa,
-                                                               uint64_t* __restrict__ ck) {
+                                                               uint64_t* __restrict__ ck, int rank_bits) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
         uint64_t q = (uint64_t)pos[a] + h;
         uint32_t r = q < n ? isa[q] + 1u : 0u;
-        ck[a] = ((uint64_t)seg[a] << 32) | r;
+        ck[a] = ((uint64_t)seg[a] << rank_bits) | r;
     }
 }
 
@@ -1283,9 +1352,10 @@ struct DoublingRankOut {
     uint32_t* isa;
     uint32_t* lcp;
     uint32_t mark;  // kLcpLowerBound | min(h, 2^31 - 1)
+    int rank_bits;
     __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const {
         isa[pos[a]] = slot[first];
-        if (a > 0 && ck[a] != ck[a - 1] && (ck[a] >> 32) == (ck[a - 1] >> 32)) lcp[slot[a]] = mark;
+        if (a > 0 && ck[a] != ck[a - 1] && (ck[a] >> rank_bits) == (ck[a - 1] >> rank_bits)) lcp[slot[a]] = mark;
     }
 };
 struct DoublingActiveIn {
