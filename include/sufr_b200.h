@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SUFR_B200_ABI_VERSION 1
+#define SUFR_B200_ABI_VERSION 2
 
 /* Return codes. */
 #define SUFR_B200_OK 0
@@ -109,6 +109,8 @@ typedef struct SufrB200Result {
     uint64_t h2d_bytes;       /* bytes this build copied host -> device (0 for a device-resident text) */
     uint64_t d2h_bytes;       /* bytes it copied device -> host: large host results travel compactly (LCP as */
                               /*   bytes + exceptions, 64-bit SA as u32) and are widened by host threads */
+    uint32_t position_bits;   /* width of text positions INSIDE the build: 32, or 64 for texts of u32::MAX bytes and */
+    uint32_t reserved2;       /*   more (suffix_array.rs:460-470; SUFR_B200_DEBUG_POS64 forces 64 on short texts) */
     void* owner;              /* internal */
 } SufrB200Result;
 

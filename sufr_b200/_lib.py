@@ -83,6 +83,8 @@ class Result(C.Structure):
         ("doubling_rounds", C.c_uint32),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("position_bits", C.c_uint32),
+        ("reserved2", C.c_uint32),
         ("owner", C.c_void_p),
     ]
 
@@ -171,7 +173,7 @@ def lib():
     L.sufr_b200_sequences_free.argtypes = [C.POINTER(Sequences)]
     L.sufr_b200_synth_dna.restype = C.c_int
     L.sufr_b200_synth_dna.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint8]
-    if L.sufr_b200_abi_version() != 1:
+    if L.sufr_b200_abi_version() != 2:
         raise LibraryMissing("libsufr_b200.so has an unexpected ABI version")
     _lib = L
     return L

@@ -64,3 +64,11 @@ def parse_sufr(data: bytes) -> SufrFile:
     assert off == len(data), (off, len(data))
     return SufrFile(version, bool(is_dna), bool(amb), bool(soft), text_len, text_pos, sa_pos, lcp_pos,
                     num_suffixes, mql, nseq, [int(s) for s in starts], mask, text, sa, lcp, names, bits)
+
+
+def parse_header(data: bytes) -> dict:
+    """The fixed part of the header (sufr_builder.rs:826-867): enough to locate the sections of a large file."""
+    text_len, text_pos, sa_pos, lcp_pos, num_suffixes, mql, nseq = struct.unpack_from("<7Q", data, 4)
+    return {"version": data[0], "is_dna": bool(data[1]), "allow_ambiguity": bool(data[2]), "ignore_softmask": bool(data[3]),
+            "text_len": text_len, "text_pos": text_pos, "sa_pos": sa_pos, "lcp_pos": lcp_pos, "num_suffixes": num_suffixes,
+            "max_query_len": mql, "num_sequences": nseq, "index_bytes": (lcp_pos - sa_pos) // max(1, num_suffixes)}

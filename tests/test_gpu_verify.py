@@ -257,3 +257,71 @@ def test_cli_devices_flag(S, tmp_path):
     assert p.returncode == 0, p.stderr
     assert out.read_bytes() == (GOLDEN / "expected" / "long_dna_sequence.sufr").read_bytes()
     assert f"on {ndev} GPU" in p.stdout
+
+
+# ------------------------------------------------------------------ 64-bit text positions (suffix_array.rs:460-470)
+POS64_CASES = {
+    "dna": (dict(is_dna=True), b"ACGTNacgtn%", 32),
+    "dna_u64": (dict(is_dna=True), b"ACGT", 64),
+    "dna_amb_soft": (dict(is_dna=True, allow_ambiguity=True, ignore_softmask=True), b"ACGTNacgtn%", 64),
+    "protein": (dict(), b"ACDEFGHIKLMNPQRSTVWY%", 64),
+    "mask": (dict(is_dna=True, seed_mask="1101101101"), b"ACGT", 32),
+    "mql": (dict(max_query_len=300), b"ACGT", 64),
+}
+
+
+@pytest.mark.parametrize("case", list(POS64_CASES))
+@pytest.mark.parametrize("world", [1, 3])
+def test_64bit_positions_forced_on_short_texts(S, monkeypatch, case, world):
+    """Texts of u32::MAX bytes and more take the 64-bit-position build (SufrBuilder::<u64>).  SUFR_B200_DEBUG_POS64
+    forces that build on short texts, where the oracle can check it entry by entry, sharded and unsharded.  (The whole
+    GPU suite also passes with the variable set: profiles/r2_gpu_suite_pos64.txt.)"""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    monkeypatch.setenv("SUFR_B200_DEBUG_POS64", "1")
+    kw, alphabet, bits = POS64_CASES[case]
+    text = rand_dna(hash(case) & 0xFFFF, 120_000, repeat_p=0.02, alphabet=alphabet)
+    want = O.oracle_build(text, num_partitions=8, threads=4, index_bits=bits, **kw)
+    shards = [S.build(S.SufrBuilderArgs(text=text, **kw), index_bits=bits, rank=r, world_size=world) for r in range(world)]
+    try:
+        assert all(int(s.c.position_bits) == 64 for s in shards)
+        meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+        offs, total = shard_layout(meta)
+        for r, s in enumerate(shards):
+            s.set_shard_layout(offs[r], total)
+            prev = previous_last_suffix(meta, r)
+            if prev is not None and s.num_suffixes:
+                s.patch_seam(prev)
+        assert total == want.num_suffixes
+        assert np.array_equal(np.concatenate([s.sa for s in shards]), want.sa)
+        assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
+    finally:
+        for s in shards:
+            s.free()
+
+
+def test_64bit_positions_deep_repeats_and_verifier(S, monkeypatch):
+    monkeypatch.setenv("SUFR_B200_DEBUG_POS64", "1")
+    text = tandem_text(11, 200_000)
+    kw = dict(is_dna=True, allow_ambiguity=True)
+    want = O.oracle_build(text, num_partitions=8, threads=4, index_bits=64, **kw)
+    r = device_build(S, text, 64, **kw)
+    try:
+        assert int(r.c.position_bits) == 64 and int(r.c.doubling_rounds) > 0
+        assert np.array_equal(r.sa_tensor().cpu().numpy().astype(np.uint64), want.sa)
+        assert np.array_equal(r.lcp_tensor().cpu().numpy().astype(np.uint64), want.lcp)
+        assert r.verify()["ok"]
+    finally:
+        r.free()
+
+
+def test_long_text_needs_shards_and_u64(S):
+    """Argument checks of the 64-bit branch: index_bits 32 is impossible, and one rank cannot hold >= 2^32 suffixes."""
+    import ctypes as C
+    from sufr_b200 import _lib
+    ctx = S.default_context(0)
+    args = S.builder._CArgs(S.SufrBuilderArgs(text=b""), text_ptr=0x1000, text_len=(1 << 32) + 5)
+    res = _lib.Result()
+    rc = _lib.lib().sufr_b200_build(ctx.handle, C.byref(args.c), 32, S.MEM_DEVICE, S.MEM_DEVICE, C.byref(res))
+    assert rc == _lib.ERR_ARGUMENT and b"index_bits 64" in _lib.lib().sufr_b200_last_error()
+    rc = _lib.lib().sufr_b200_build(ctx.handle, C.byref(args.c), 0, S.MEM_DEVICE, S.MEM_DEVICE, C.byref(res))
+    assert rc == _lib.ERR_UNSUPPORTED and b"key-range shards" in _lib.lib().sufr_b200_last_error()

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(S):
     L = _lib.lib()
     for sym in declared:
         assert getattr(L, sym) is not None
-    assert L.sufr_b200_abi_version() == 1
+    assert L.sufr_b200_abi_version() == 2
     out = subprocess.check_output(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], text=True)
     exported = set(re.findall(r" T (sufr_b200_[a-z0-9_]+)", out))
     assert set(declared) <= exported
