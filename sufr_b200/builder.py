@@ -342,7 +342,9 @@ def create_multi(args: SufrBuilderArgs, devices: Sequence[int], index_bits: int 
     try:
         return {"num_suffixes": int(res.num_suffixes), "text_len": int(res.text_len), "index_bits": int(res.index_bits),
                 "timings": res.timings.as_dict(), "kernel_launches": int(res.kernel_launches),
-                "text": C.string_at(res.text, res.text_len) if res.text else b"",
+                # (ctypes.string_at takes a C int: texts of 2 GiB and more go through numpy)
+                "text": np.ctypeslib.as_array(C.cast(res.text, C.POINTER(C.c_uint8)), (int(res.text_len),)).tobytes()
+                if res.text and res.text_len else b"",
                 "n_ranges": [(int(res.n_ranges[2 * i]), int(res.n_ranges[2 * i + 1])) for i in range(res.num_n_ranges)]}
     finally:
         _lib.lib().sufr_b200_result_free(None, C.byref(res))

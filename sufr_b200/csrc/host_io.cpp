@@ -1,6 +1,8 @@
 #include "host_io.hpp"
 
+#include <dlfcn.h>
 #include <fcntl.h>
+#include <zlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -179,9 +181,16 @@ void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
 // behaviour for plain-text input: FASTA records may span lines, FASTQ records are 4 lines, '\r' is
 // stripped at line ends, the id is the header up to the first whitespace.
 //
-// FASTA is parsed by all host cores: the file is read with parallel preads, cut into slices at line starts, and
-// every slice is handled in two passes (count, then write at its final offset), so a 3 Gbp genome is ingested at
-// memory speed instead of by one core.  FASTQ (line roles depend on the line number) stays serial.
+// Compressed input (needletail decompresses gz / bz2 / xz / zstd transparently): detected by magic bytes and inflated
+// in memory -- gzip through zlib (multi-member files included), the other three through the system's runtime
+// libraries (libbz2.so.1.0, liblzma.so.5, libzstd.so.1; loaded on demand, a clear error when one is missing).
+//
+// Both formats are parsed by all host cores: the file is read with parallel preads, cut into slices at record
+// boundaries that can be recognised locally, and every slice is handled in two passes (count, then write at its
+// final offset), so a 3 Gbp genome is ingested at memory speed instead of by one core.  FASTA slices start at any
+// line start; a FASTQ slice starts at a line that begins with '@' and whose second successor begins with '+' (in a
+// four-line record only the header satisfies both: a quality line that begins with '@' is followed by a header and
+// then by a sequence line, which cannot begin with '+').
 namespace {
 
 struct FileData {
@@ -209,7 +218,168 @@ void parallel_for(int threads, F f) {
     for (auto& e : err) if (e) std::rethrow_exception(e);
 }
 
+// ---- decompression
+struct Inflated {
+    char* p = nullptr;
+    size_t n = 0, cap = 0;
+    void need(size_t extra) {
+        if (n + extra <= cap) return;
+        size_t c = std::max<size_t>(cap * 2, n + extra + (1u << 20));
+        char* q = (char*)realloc(p, c);
+        if (!q) { free(p); p = nullptr; throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, "out of host memory while decompressing"); }
+        p = q;
+        cap = c;
+    }
+};
+
+void inflate_gzip(const char* path, const char* src, size_t n, Inflated& out) {
+    size_t pos = 0;
+    while (pos < n) {  // one iteration per gzip member (bgzip and `cat a.gz b.gz` files have many)
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) throw Error(SUFR_B200_ERR_INTERNAL, "zlib: inflateInit2 failed");
+        int rc = Z_OK;
+        while (rc != Z_STREAM_END) {
+            out.need(4u << 20);
+            zs.next_in = (Bytef*)(src + pos);
+            zs.avail_in = (uInt)std::min<size_t>(n - pos, 1u << 30);
+            zs.next_out = (Bytef*)(out.p + out.n);
+            zs.avail_out = (uInt)std::min<size_t>(out.cap - out.n, 1u << 30);
+            const uInt in0 = zs.avail_in, out0 = zs.avail_out;
+            rc = inflate(&zs, Z_NO_FLUSH);
+            pos += in0 - zs.avail_in;
+            out.n += out0 - zs.avail_out;
+            if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) {
+                inflateEnd(&zs);
+                throw Error(SUFR_B200_ERR_IO, std::string(path) + ": corrupt gzip data (" + (zs.msg ? zs.msg : "zlib error") + ")");
+            }
+            if (rc != Z_STREAM_END && pos >= n && in0 == zs.avail_in && out0 == zs.avail_out) {
+                inflateEnd(&zs);
+                throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated gzip data");
+            }
+        }
+        inflateEnd(&zs);
+        while (pos < n && src[pos] == 0) pos++;  // zero padding between / behind members
+    }
+}
+
+void* runtime_lib(const char* path, const char* const* names) {
+    for (; *names; names++)
+        if (void* h = dlopen(*names, RTLD_NOW | RTLD_GLOBAL)) return h;
+    throw Error(SUFR_B200_ERR_UNSUPPORTED, std::string(path) + ": this input needs a decompression library that is not installed");
+}
+template <typename F>
+F runtime_sym(void* lib, const char* name) {
+    void* f = dlsym(lib, name);
+    if (!f) throw Error(SUFR_B200_ERR_UNSUPPORTED, std::string("missing symbol ") + name);
+    return reinterpret_cast<F>(f);
+}
+
+void inflate_zstd(const char* path, const char* src, size_t n, Inflated& out) {
+    static const char* const names[] = {"libzstd.so.1", "libzstd.so", nullptr};
+    void* lib = runtime_lib(path, names);
+    auto content_size = runtime_sym<unsigned long long (*)(const void*, size_t)>(lib, "ZSTD_getFrameContentSize");
+    auto frame_size = runtime_sym<size_t (*)(const void*, size_t)>(lib, "ZSTD_findFrameCompressedSize");
+    auto decompress = runtime_sym<size_t (*)(void*, size_t, const void*, size_t)>(lib, "ZSTD_decompress");
+    auto is_error = runtime_sym<unsigned (*)(size_t)>(lib, "ZSTD_isError");
+    size_t pos = 0;
+    while (pos < n) {  // one iteration per frame
+        const size_t fs = frame_size(src + pos, n - pos);
+        if (is_error(fs)) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": corrupt zstd data");
+        unsigned long long cs = content_size(src + pos, fs);
+        size_t guess = cs < (1ull << 62) ? (size_t)cs : fs * 8 + (1u << 20);  // unknown size: grow until it fits
+        for (;;) {
+            out.need(guess);
+            const size_t got = decompress(out.p + out.n, out.cap - out.n, src + pos, fs);
+            if (!is_error(got)) { out.n += got; break; }
+            if (cs < (1ull << 62) || guess > (1ull << 40)) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": corrupt zstd data");
+            guess *= 2;
+        }
+        pos += fs;
+    }
+}
+
+void inflate_bzip2(const char* path, const char* src, size_t n, Inflated& out) {
+    static const char* const names[] = {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so", nullptr};
+    void* lib = runtime_lib(path, names);
+    // bz_stream of bzlib.h 1.0.x
+    struct BzStream {
+        char* next_in; unsigned avail_in, total_in_lo32, total_in_hi32;
+        char* next_out; unsigned avail_out, total_out_lo32, total_out_hi32;
+        void* state; void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+    };
+    auto init = runtime_sym<int (*)(BzStream*, int, int)>(lib, "BZ2_bzDecompressInit");
+    auto step = runtime_sym<int (*)(BzStream*)>(lib, "BZ2_bzDecompress");
+    auto end = runtime_sym<int (*)(BzStream*)>(lib, "BZ2_bzDecompressEnd");
+    size_t pos = 0;
+    while (pos < n) {  // one iteration per stream
+        BzStream bz;
+        memset(&bz, 0, sizeof(bz));
+        if (init(&bz, 0, 0) != 0) throw Error(SUFR_B200_ERR_INTERNAL, "bzip2: init failed");
+        int rc = 0;
+        while (rc != 4 /* BZ_STREAM_END */) {
+            out.need(4u << 20);
+            bz.next_in = const_cast<char*>(src + pos);
+            bz.avail_in = (unsigned)std::min<size_t>(n - pos, 1u << 30);
+            bz.next_out = out.p + out.n;
+            bz.avail_out = (unsigned)std::min<size_t>(out.cap - out.n, 1u << 30);
+            const unsigned in0 = bz.avail_in, out0 = bz.avail_out;
+            rc = step(&bz);
+            pos += in0 - bz.avail_in;
+            out.n += out0 - bz.avail_out;
+            if (rc != 0 && rc != 4) { end(&bz); throw Error(SUFR_B200_ERR_IO, std::string(path) + ": corrupt bzip2 data"); }
+            if (rc != 4 && pos >= n && in0 == bz.avail_in && out0 == bz.avail_out) {
+                end(&bz);
+                throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated bzip2 data");
+            }
+        }
+        end(&bz);
+    }
+}
+
+void inflate_xz(const char* path, const char* src, size_t n, Inflated& out) {
+    static const char* const names[] = {"liblzma.so.5", "liblzma.so", nullptr};
+    void* lib = runtime_lib(path, names);
+    // lzma_stream_buffer_decode(memlimit, flags, allocator, in, in_pos, in_size, out, out_pos, out_size)
+    auto decode = runtime_sym<int (*)(uint64_t*, uint32_t, const void*, const uint8_t*, size_t*, size_t, uint8_t*, size_t*, size_t)>(
+        lib, "lzma_stream_buffer_decode");
+    size_t guess = n * 6 + (1u << 20);
+    for (;;) {
+        out.n = 0;
+        out.need(guess);
+        uint64_t memlimit = ~0ull;
+        size_t in_pos = 0, out_pos = 0;
+        const int rc = decode(&memlimit, 0x08 /* LZMA_CONCATENATED */, nullptr, (const uint8_t*)src, &in_pos, n, (uint8_t*)out.p,
+                              &out_pos, out.cap);
+        if (rc == 0) { out.n = out_pos; return; }
+        // LZMA_BUF_ERROR (10) means "output too small" -- or, when output space is left, that the input ends early
+        if (rc == 10 && out_pos < out.cap) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated xz data");
+        if (rc != 10 || guess > (1ull << 40)) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": corrupt xz data");
+        guess *= 2;
+    }
+}
+
+// replaces a compressed file image by its content
+void maybe_decompress(const char* path, char*& p, size_t& n) {
+    const unsigned char* u = (const unsigned char*)p;
+    Inflated out;
+    if (n >= 2 && u[0] == 0x1F && u[1] == 0x8B) inflate_gzip(path, p, n, out);
+    else if (n >= 4 && u[0] == 0x28 && u[1] == 0xB5 && u[2] == 0x2F && u[3] == 0xFD) inflate_zstd(path, p, n, out);
+    else if (n >= 3 && u[0] == 'B' && u[1] == 'Z' && u[2] == 'h') inflate_bzip2(path, p, n, out);
+    else if (n >= 6 && u[0] == 0xFD && u[1] == '7' && u[2] == 'z' && u[3] == 'X' && u[4] == 'Z' && u[5] == 0) inflate_xz(path, p, n, out);
+    else return;
+    free(p);
+    p = out.p;
+    n = out.n;
+}
+
+void load_file_raw(const char* path, FileData& d);
 void load_file(const char* path, FileData& d) {
+    load_file_raw(path, d);
+    maybe_decompress(path, d.p, d.n);
+}
+
+void load_file_raw(const char* path, FileData& d) {
     int fd = open(path, O_RDONLY);
     if (fd < 0) throw Error(SUFR_B200_ERR_IO, std::string(path) + ": " + strerror(errno));
     struct stat st;
@@ -351,25 +521,85 @@ void read_sequence_file(const char* path, uint8_t delim, SufrB200Sequences* out)
             }
         }
     } else {
-        std::vector<uint8_t> buf;
-        buf.reserve(n / 2 + 1);
-        size_t pos = 0, b, e;
-        uint64_t i = 0;
-        while (next_line(data, n, pos, b, e)) {
-            if (e == b) continue;
-            if (i > 0) buf.push_back(delim);
-            starts.push_back(buf.size());
-            i += 1;
-            names.push_back(record_name(data, b + 1, e, i));
-            size_t sb, se, xb, xe;
-            if (!next_line(data, n, pos, sb, se) || !next_line(data, n, pos, xb, xe) || !next_line(data, n, pos, xb, xe))
-                throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated FASTQ record");
-            buf.insert(buf.end(), data + sb, data + se);
+        // FASTQ: four lines per record (header, sequence, '+' line, qualities)
+        auto line_start = [&](size_t p) {  // first line start at or behind p
+            if (p == 0 || p >= n || data[p - 1] == '\n') return std::min(p, n);
+            const void* nl = memchr(data + p, '\n', n - p);
+            return nl ? (size_t)((const char*)nl - data) + 1 : n;
+        };
+        auto is_record_start = [&](size_t p) {  // '@' line whose second successor is a '+' line
+            if (p >= n || data[p] != '@') return false;
+            size_t pos = p, b, e;
+            if (!next_line(data, n, pos, b, e) || !next_line(data, n, pos, b, e)) return false;
+            return pos < n && data[pos] == '+';
+        };
+        int T = ingest_threads(n);
+        std::vector<Slice> sl(T);
+        for (int t = 0; t < T; t++) {
+            size_t lo = t == 0 ? 0 : line_start(n * (size_t)t / T);
+            for (int tries = 0; t > 0 && lo < n && !is_record_start(lo) && tries < 8; tries++) {
+                size_t pos = lo, b, e;
+                next_line(data, n, pos, b, e);
+                lo = pos;
+            }
+            if (t > 0 && lo < n && !is_record_start(lo)) lo = n;  // malformed neighbourhood: leave it to the slice before
+            sl[t].lo = std::min(lo, n);
+            if (t > 0) {
+                if (sl[t].lo < sl[t - 1].lo) sl[t].lo = sl[t - 1].lo;
+                sl[t - 1].hi = sl[t].lo;
+            }
         }
-        buf.push_back('$');
-        seq_len = buf.size();
+        sl[T - 1].hi = n;
+        parallel_for(T, [&](int t) {  // pass 1: sizes
+            Slice& c = sl[t];
+            size_t pos = c.lo, b, e;
+            while (pos < c.hi && next_line(data, n, pos, b, e)) {
+                if (e == b) continue;
+                size_t sb, se, xb, xe;
+                if (!next_line(data, n, pos, sb, se) || !next_line(data, n, pos, xb, xe) || !next_line(data, n, pos, xb, xe))
+                    throw Error(SUFR_B200_ERR_IO, std::string(path) + ": truncated FASTQ record");
+                c.headers++;
+                c.header_lines.push_back({b + 1, e});
+                c.seq_bytes += se - sb;
+            }
+        });
+        uint64_t off = 0, rec = 0;
+        for (int t = 0; t < T; t++) {
+            sl[t].out_off = off;
+            sl[t].first_record = rec;
+            off += sl[t].seq_bytes + sl[t].headers;
+            rec += sl[t].headers;
+        }
+        seq_len = rec ? off : 1;  // delimiters between records + the sentinel = one byte per record
         seq = (uint8_t*)malloc(seq_len);
-        memcpy(seq, buf.data(), seq_len);
+        if (!seq) throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, std::string(path) + ": out of host memory");
+        parallel_for(T, [&](int t) {  // pass 2
+            Slice& c = sl[t];
+            uint64_t o = c.out_off - (c.first_record > 0 ? 1 : 0);
+            uint64_t ordinal = c.first_record;
+            size_t pos = c.lo, b, e;
+            while (pos < c.hi && next_line(data, n, pos, b, e)) {
+                if (e == b) continue;
+                size_t sb = 0, se = 0, xb, xe;
+                next_line(data, n, pos, sb, se);
+                next_line(data, n, pos, xb, xe);
+                next_line(data, n, pos, xb, xe);
+                if (ordinal > 0) seq[o++] = delim;
+                c.starts.push_back(o);
+                ordinal++;
+                memcpy(seq + o, data + sb, se - sb);
+                o += se - sb;
+            }
+        });
+        seq[seq_len - 1] = '$';
+        for (int t = 0; t < T; t++) {
+            uint64_t ordinal = sl[t].first_record;
+            for (size_t k = 0; k < sl[t].starts.size(); k++) {
+                starts.push_back(sl[t].starts[k]);
+                ordinal++;
+                names.push_back(record_name(data, sl[t].header_lines[k].first, sl[t].header_lines[k].second, ordinal));
+            }
+        }
     }
 
     out->seq_len = seq_len;

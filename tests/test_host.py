@@ -169,6 +169,61 @@ def test_parallel_fasta_ingest_matches_serial_restatement(S, tmp_path, seed, rec
     assert a.seq == b.seq
 
 
+@pytest.mark.parametrize("codec", ["gz", "gz_multi_member", "bz2", "xz", "zst"])
+def test_compressed_input(S, tmp_path, codec):
+    """needletail decompresses gz / bz2 / xz / zstd transparently (util.rs:55); so does read_sequence_file here."""
+    import bz2, gzip, lzma, random
+    rng = random.Random(5)
+    fa = tmp_path / "t.fa"
+    with open(fa, "w") as f:
+        for r in range(300):
+            f.write(f">seq{r} description\n")
+            body = "".join(rng.choice("ACGTN") for _ in range(rng.randrange(1, 5000)))
+            for i in range(0, len(body), 70):
+                f.write(body[i:i + 70] + "\n")
+    raw = fa.read_bytes()
+    if codec == "gz":
+        blob = gzip.compress(raw)
+    elif codec == "gz_multi_member":  # what bgzip and `cat a.gz b.gz` produce
+        blob = gzip.compress(raw[:len(raw) // 3]) + gzip.compress(raw[len(raw) // 3:])
+    elif codec == "bz2":
+        blob = bz2.compress(raw)
+    elif codec == "xz":
+        blob = lzma.compress(raw)
+    else:
+        pa = pytest.importorskip("pyarrow")
+        blob = pa.compress(raw, codec="zstd", asbytes=True)
+    packed = tmp_path / f"t.fa.{codec}"
+    packed.write_bytes(blob)
+    want = O.read_sequence_file(fa, b"%")
+    got = S.read_sequence_file(packed, b"%")
+    assert (got.seq, got.start_positions, got.sequence_names) == (want.seq, want.start_positions, want.sequence_names)
+    packed.write_bytes(blob[:len(blob) // 2])
+    with pytest.raises(S.SufrError, match="truncated|corrupt"):
+        S.read_sequence_file(packed, b"%")
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_parallel_fastq_ingest_matches_serial_restatement(S, tmp_path, crlf):
+    """FASTQ is parsed by several threads too: a slice starts at an '@' line whose second successor is a '+' line --
+    qualities that begin with '@' or '+' must not confuse it."""
+    import random
+    rng = random.Random(11)
+    eol = "\r\n" if crlf else "\n"
+    fq = tmp_path / "big.fq"
+    with open(fq, "w", newline="") as f:
+        for r in range(150_000):
+            seq = "".join(rng.choice("ACGTN") for _ in range(rng.randrange(20, 150)))
+            qual = "".join(rng.choice("@+IJ#5") for _ in range(len(seq)))
+            f.write(f"@read{r} extra{eol}{seq}{eol}+{eol}{qual}{eol}")
+    assert fq.stat().st_size > 20_000_000  # several slices
+    want = O.read_sequence_file(fq, b"%")
+    got = S.read_sequence_file(fq, b"%")
+    assert got.start_positions == want.start_positions
+    assert got.sequence_names == want.sequence_names
+    assert got.seq == want.seq
+
+
 def test_create_rejects_sharded_arguments(S):
     from sufr_b200 import _lib
     import ctypes as C

@@ -82,6 +82,7 @@ def main():
     r = rep.as_dict()
     errors = r["order_errors"] + r["lcp_errors"] + r["out_of_range"] + r["not_indexed"] + r["duplicates"]
     same_text = bool(torch.equal(text.cpu(), torch.from_numpy(h_text)))  # --dna on uppercase ACGT: transform is identity
+    same_text = same_text and info["text"] == h_text.tobytes()             # and the builder's `text` field
     print(json.dumps({
         "what": f"sufr_b200_create_multi: {a.bases} bp synthetic genome in 24 records, u{8 * w} SA + LCP, {a.gpus} GPU(s), "
                 f"host text -> one .sufr file at {a.out}",
