@@ -679,26 +679,67 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     }
     keys_sorted.reset();
     unsigned long long tot = 0;
-    // A large unresolved fraction after the first sort means a repetitive text: it will need prefix doubling,
+    // An unresolved MAJORITY after the first sort means a text of tandem repeats: it will need prefix doubling,
     // which needs every position.  Give up this (filtered / sharded) attempt now rather than after the
     // patient word rounds.
-    if (!full_set_ && ks.mode == kModeFull && m * 16 >= r0n) throw NeedFullSort{};
+    if (!full_set_ && ks.mode == kModeFull && m * 2 >= r0n) throw NeedFullSort{};
 
     // Full sort: after kMaxWordRounds words switch to prefix doubling (depth doubles per round).
     // When this attempt sorts only a subset of the positions (filter applied up front / one shard), doubling
-    // means redoing the build over all positions, so shallow repeats (few unresolved elements) get more
-    // word rounds first.
-    const int kMaxWordRounds = 3, kPatientWordRounds = 48;
+    // means redoing the build over all positions -- on every rank of a multi-GPU build.  Dispersed repeats (copies of
+    // earlier segments with some divergence, as in real genomes and BASELINE's repetitive variant) resolve a good
+    // share of what is left with every further word, and the cost of a round falls with it: such an attempt stays
+    // with word rounds (up to 320 words = 6720 bases) while they pay, so a shard finishes on its own and N GPUs
+    // divide the work.  Tandem repeats make no progress per word and leave for prefix doubling at once.
+    const int kMaxWordRounds = 3, kPatientWordRounds = 320;
+    uint64_t m_last = m;  // unresolved elements at the start of the previous round
+    int direct_tail_word = -1;
     while (m > 0) {
         if (ks.mode == kModeFull && word >= kMaxWordRounds) {
-            bool patient = !full_set_ && word < kPatientWordRounds && m * 16 < s;
+            bool patient = !full_set_ && word < kPatientWordRounds && (m * 16 < s || m * 16 <= m_last * 15);
             if (!patient) {
                 doubling(slot, pos, seg, m, nseg, (uint64_t)(word + 1) * K);
                 return;
             }
         }
+        // The deep tail of a subset attempt: few elements left, mostly pairs (a segment and its copy) that would take
+        // one launch-bound round per further key word.  Finish the small groups by direct comparison.
+        // (Not in every round: groups of more than eight members keep going through word rounds and shed small groups as
+        // they split; a sweep every 16 words collects those.)
+        if (ks.mode == kModeFull && !full_set_ && word >= kMaxWordRounds && m * 32 <= s && !sentinel_ &&
+            (direct_tail_word < 0 || word - direct_tail_word >= 16) && !getenv("SUFR_B200_DEBUG_NO_DIRECT_TAIL")) {
+            direct_tail_word = word;
+            auto is_large = dalloc<uint8_t>(nseg ? nseg : 1);
+            auto d_left = dalloc<unsigned long long>(1);
+            SUFR_CUDA_CHECK(cudaMemsetAsync(is_large.get(), 0, nseg ? nseg : 1, st()));
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_left.get(), 0, 8, st()));
+            finish_small_groups_kernel<<<grid_for(m, 1), kBlock, 0, st()>>>(ks, m, (uint64_t)(word + 1) * K, seg.get(), slot.get(),
+                                                                           pos.get(), d_sa.get(), d_lcp.get(), is_large.get(),
+                                                                           d_left.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+            unsigned long long left = 0;
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(&left, d_left.get(), 8, cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            if (left == 0) return;
+            DevBuf<unsigned long long> part;
+            LargeIn lin{seg.get(), is_large.get()};
+            const unsigned long long lt = scan_begin(m, lin, scan::SumU64{}, part);
+            const uint64_t m2 = (uint32_t)lt, nseg2 = lt >> 32;
+            auto slot2 = dalloc<uint32_t>(m2);
+            auto pos2 = dalloc<pos_t>(m2);
+            auto seg2 = dalloc<uint32_t>(m2);
+            scan_finish(m, lin, scan::SumU64{}, LeftoverOut{slot.get(), pos.get(), slot2.get(), pos2.get(), seg2.get()}, part);
+            slot = std::move(slot2);
+            pos = std::move(pos2);
+            seg = std::move(seg2);
+            m = m2;
+            nseg = nseg2;
+            if (m == 0) return;
+        }
         word++;
         refine_rounds++;
+        m_last = m;
         if (getenv("SUFR_B200_LOG_ROUNDS")) {
             SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
             fprintf(stderr, "[sufr_b200] word round %u (key word %d): unresolved = %llu in %llu groups, t = %.3f s\n",

@@ -250,8 +250,17 @@ static void free_owner(ResultOwner* o) {
     delete o;
 }
 
+// Every entry point leaves the calling thread's current CUDA device as it found it (the library switches to the
+// device of the context / of each shard inside; frameworks such as torch cache the current device per thread).
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <typename F>
 static int guarded(F&& f) {
+    DeviceRestore restore;
     try {
         f();
         return SUFR_B200_OK;
@@ -272,9 +281,9 @@ static int guarded(F&& f) {
 // suffix / LCP arrays is ever allocated (page-locking 2 * s * sizeof(T) bytes costs seconds by itself).
 class StreamWriter {
    public:
-    StreamWriter(int fd, const std::string& path, int device, cudaStream_t stream, size_t slot_bytes = 64u << 20, int nslots = 6,
+    StreamWriter(OutputFile& file, int device, cudaStream_t stream, size_t slot_bytes = 64u << 20, int nslots = 6,
                  int nworkers = 4)
-        : fd_(fd), path_(path), device_(device), stream_(stream), slot_bytes_(slot_bytes) {
+        : file_(file), device_(device), stream_(stream), slot_bytes_(slot_bytes) {
         try {
             for (int i = 0; i < nslots; i++) {
                 Slot sl{nullptr, nullptr};
@@ -358,7 +367,7 @@ class StreamWriter {
                 cudaError_t e = cudaEventSynchronize(slots_[j.slot].ev);
                 if (e != cudaSuccess) throw Error(100 + (int)e, std::string("CUDA error in the file writer: ") + cudaGetErrorString(e));
                 if (j.host_copy) memcpy(j.host_copy, slots_[j.slot].buf, j.len);
-                pwrite_all(fd_, slots_[j.slot].buf, j.len, j.off, path_);
+                file_.write(j.off, slots_[j.slot].buf, j.len);
             } catch (...) {
                 std::lock_guard<std::mutex> lock(mu_);
                 if (!err_) err_ = std::current_exception();
@@ -370,8 +379,7 @@ class StreamWriter {
             cv_free_.notify_one();
         }
     }
-    int fd_;
-    std::string path_;
+    OutputFile& file_;
     int device_;
     cudaStream_t stream_;
     size_t slot_bytes_;
@@ -394,8 +402,7 @@ static void stream_result_to_file(Ctx& ctx, const SufrB200Args& args, const Sufr
     const SufrFrame f = make_sufr_frame(args, r.index_bits, r.text_len, r.total_suffixes);
     const bool sharded = args.world_size > 1;
     const bool leader = !sharded || args.rank == 0;
-    int fd = open(path.c_str(), O_WRONLY | O_CREAT | (sharded ? 0 : O_TRUNC), 0644);
-    if (fd < 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));  // sufr_builder.rs:820
+    OutputFile out(path, f.names_pos + f.tail.size(), !sharded);
     uint8_t* text = nullptr;
     try {
         if (leader) {  // ranks > 0 of a sharded build neither write nor return the text
@@ -403,30 +410,27 @@ static void stream_result_to_file(Ctx& ctx, const SufrB200Args& args, const Sufr
             if (!text) throw Error(SUFR_B200_ERR_OUT_OF_MEMORY, "out of host memory for the transformed text");
         }
         {
-            // page-cache / tmpfs writes are CPU bound (page allocation + copy, ~1 GB/s per thread): many writers on
-            // many small slots, shared fairly between the ranks of a multi-GPU build
+            // page-cache / tmpfs writes are CPU bound (page allocation + copy): many writers on many small slots,
+            // shared fairly between the ranks of a multi-GPU build
             const int hw = (int)std::thread::hardware_concurrency();
             const int share = std::max(1, (int)args.world_size);
             int workers = std::max(2, std::min(24, (hw - 2) / share));
             if (const char* dbg = getenv("SUFR_B200_WRITER_THREADS")) workers = std::max(1, atoi(dbg));
-            StreamWriter sw(fd, path, ctx.device, ctx.stream, 16u << 20, workers + 4, workers);
+            StreamWriter sw(out, ctx.device, ctx.stream, 16u << 20, workers + 4, workers);
             if (leader) {
-                pwrite_all(fd, f.head.data(), f.head.size(), 0, path);
-                pwrite_all(fd, f.tail.data(), f.tail.size(), f.names_pos, path);
-                if (sharded && ftruncate(fd, (off_t)(f.names_pos + f.tail.size())) != 0)
-                    throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
+                out.write(0, f.head.data(), f.head.size());
+                out.write(f.names_pos, f.tail.data(), f.tail.size());
+                sw.submit(r.text, r.text_len, f.text_pos, text);
             }
-            if (leader) sw.submit(r.text, r.text_len, f.text_pos, text);
             sw.submit(r.sa, r.num_suffixes * w, f.sa_pos + r.shard_offset * w);
             sw.submit(r.lcp, r.num_suffixes * w, f.lcp_pos + r.shard_offset * w);
             sw.finish();
         }
+        out.close();
     } catch (...) {
-        close(fd);
         free(text);
         throw;
     }
-    if (close(fd) != 0) { free(text); throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno)); }
     if (host_text) *host_text = text; else free(text);
 }
 

@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <zlib.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -127,20 +128,60 @@ SufrFrame make_sufr_frame(const SufrB200Args& args, uint32_t index_bits, uint64_
     return f;
 }
 
-// A section of tens of GB written by several threads (page-cache copies are CPU bound; disks like a deep queue).
-static void pwrite_parallel(int fd, const void* buf, size_t len, uint64_t off, const std::string& path) {
-    size_t piece = 256u << 20;
+OutputFile::OutputFile(const std::string& path, uint64_t final_size, bool truncate_existing) : path_(path), size_(final_size) {
+    fd_ = open(path.c_str(), O_RDWR | O_CREAT | (truncate_existing ? O_TRUNC : 0), 0644);
+    if (fd_ < 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));  // sufr_builder.rs:820
+    // every writer (rank) sets the same final size: idempotent, and no rank has to wait for another one
+    if (ftruncate(fd_, (off_t)final_size) != 0) {
+        const std::string msg = path + ": " + strerror(errno);
+        ::close(fd_);
+        fd_ = -1;
+        throw Error(SUFR_B200_ERR_IO, msg);
+    }
+    if (final_size && !getenv("SUFR_B200_DEBUG_NO_MMAP")) {
+        void* m = mmap(nullptr, final_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, 0);
+        if (m != MAP_FAILED) map_ = (uint8_t*)m;
+    }
+}
+
+OutputFile::~OutputFile() {
+    if (map_) munmap(map_, size_);
+    if (fd_ >= 0) ::close(fd_);
+}
+
+void OutputFile::close() {
+    if (map_) {
+        if (munmap(map_, size_) != 0) { map_ = nullptr; throw Error(SUFR_B200_ERR_IO, path_ + ": " + strerror(errno)); }
+        map_ = nullptr;
+    }
+    if (fd_ >= 0) {
+        const int rc = ::close(fd_);
+        fd_ = -1;
+        if (rc != 0) throw Error(SUFR_B200_ERR_IO, path_ + ": " + strerror(errno));
+    }
+}
+
+void OutputFile::write(uint64_t off, const void* buf, size_t len) {
+    if (len == 0) return;
+    if (off + len > size_) throw Error(SUFR_B200_ERR_INTERNAL, path_ + ": write beyond the planned file size");
+    if (map_) memcpy(map_ + off, buf, len);
+    else pwrite_all(fd_, buf, len, off, path_);
+}
+
+// A section of tens of GB copied by several threads (page-cache copies are CPU bound: page allocation + memcpy).
+void OutputFile::write_parallel(uint64_t off, const void* buf, size_t len) {
+    size_t piece = 64u << 20;
     if (const char* dbg = getenv("SUFR_B200_DEBUG_WRITE_PIECE")) piece = std::max<size_t>(1, strtoull(dbg, nullptr, 10));
     size_t T = std::thread::hardware_concurrency();
-    T = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(T, 8), len / piece));
-    if (T <= 1) { pwrite_all(fd, buf, len, off, path); return; }
+    T = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(T, 24), len / piece));
+    if (T <= 1) { write(off, buf, len); return; }
     std::vector<std::thread> pool;
     std::vector<std::exception_ptr> err(T);
     for (size_t t = 0; t < T; t++)
         pool.emplace_back([&, t]() {
             try {
                 const size_t lo = len * t / T, hi = len * (t + 1) / T;
-                pwrite_all(fd, (const char*)buf + lo, hi - lo, off + lo, path);
+                write(off + lo, (const char*)buf + lo, hi - lo);
             } catch (...) { err[t] = std::current_exception(); }
         });
     for (auto& th : pool) th.join();
@@ -151,29 +192,17 @@ void write_sufr_file(const SufrB200Args& args, const SufrB200Result& r) {
     const std::string path = args.path ? args.path : "out.sufr";  // sufr_builder.rs:215
     const size_t w = r.index_bits / 8;
     const SufrFrame f = make_sufr_frame(args, r.index_bits, r.text_len, r.total_suffixes);
-    const std::vector<uint8_t>& head = f.head;
-    const std::vector<uint8_t>& tail = f.tail;
-    const uint64_t text_pos = f.text_pos, sa_pos = f.sa_pos, lcp_pos = f.lcp_pos, names_pos = f.names_pos;
-
     const bool sharded = args.world_size > 1;
     const bool leader = !sharded || args.rank == 0;
-    int fd = open(path.c_str(), O_WRONLY | O_CREAT | (sharded ? 0 : O_TRUNC), 0644);
-    if (fd < 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));  // sufr_builder.rs:820
-    try {
-        if (leader) {
-            pwrite_all(fd, head.data(), head.size(), 0, path);
-            pwrite_parallel(fd, r.text, r.text_len, text_pos, path);
-            pwrite_all(fd, tail.data(), tail.size(), names_pos, path);
-            if (sharded && ftruncate(fd, (off_t)(names_pos + tail.size())) != 0)
-                throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
-        }
-        pwrite_parallel(fd, r.sa, r.num_suffixes * w, sa_pos + r.shard_offset * w, path);
-        pwrite_parallel(fd, r.lcp, r.num_suffixes * w, lcp_pos + r.shard_offset * w, path);
-    } catch (...) {
-        close(fd);
-        throw;
+    OutputFile out(path, f.names_pos + f.tail.size(), !sharded);
+    if (leader) {
+        out.write(0, f.head.data(), f.head.size());
+        out.write_parallel(f.text_pos, r.text, r.text_len);
+        out.write(f.names_pos, f.tail.data(), f.tail.size());
     }
-    if (close(fd) != 0) throw Error(SUFR_B200_ERR_IO, path + ": " + strerror(errno));
+    out.write_parallel(f.sa_pos + r.shard_offset * w, r.sa, r.num_suffixes * w);
+    out.write_parallel(f.lcp_pos + r.shard_offset * w, r.lcp, r.num_suffixes * w);
+    out.close();
 }
 
 // ------------------------------------------------------------------ FASTA / FASTQ ingest (util.rs:51-89)

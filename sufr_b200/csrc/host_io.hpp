@@ -30,6 +30,28 @@ struct SufrFrame {
 SufrFrame make_sufr_frame(const SufrB200Args& args, uint32_t index_bits, uint64_t text_len, uint64_t total_suffixes);
 void pwrite_all(int fd, const void* buf, size_t len, uint64_t off, const std::string& path);
 
+// The output file of a build, written by many threads (and, sharded, by several ranks) at known offsets.  Concurrent
+// pwrite()s to ONE file serialise on the inode lock (3.5 GB/s on a RAM disk, whatever the thread count), so the file is
+// sized up front and mapped: the writers copy into the mapping and fault its pages in parallel.  Falls back to pwrite
+// where the file cannot be mapped.
+class OutputFile {
+   public:
+    OutputFile(const std::string& path, uint64_t final_size, bool truncate_existing);
+    ~OutputFile();
+    OutputFile(const OutputFile&) = delete;
+    OutputFile& operator=(const OutputFile&) = delete;
+    void write(uint64_t off, const void* buf, size_t len);            // thread-safe for disjoint ranges
+    void write_parallel(uint64_t off, const void* buf, size_t len);   // a large section, copied by several threads
+    void close();                                                     // reports errors; the destructor does not
+    bool mapped() const { return map_ != nullptr; }
+
+   private:
+    std::string path_;
+    int fd_ = -1;
+    uint8_t* map_ = nullptr;
+    uint64_t size_ = 0;
+};
+
 // util.rs:51-89
 void read_sequence_file(const char* path, uint8_t delim, SufrB200Sequences* out);
 void free_sequences(SufrB200Sequences* s);

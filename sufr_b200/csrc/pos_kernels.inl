@@ -978,6 +978,75 @@ __global__ void __launch_bounds__(kBlock) small_groups_kernel(uint64_t m, const 
         }
     }
 }
+// Full sort, few unresolved elements left (the deep tail of a repetitive text): groups of at most kSmallSeg members
+// are finished in ONE step by comparing their suffixes directly from the depth they are known to share -- instead of
+// one launch-bound round per key word (a 4 kb repeat is 200 words deep).  The thread at the group start insertion-
+// sorts the members, writes the final order into the suffix array and the exact LCP of every new boundary, and
+// clears the members' "continues the group" marks; larger groups are left to further rounds (flag in is_large).
+__device__ __forceinline__ bool suffix_less(const KeySpec& ks, uint64_t pa, uint64_t pb, uint64_t depth, uint64_t& lcp_out) {
+    const uint64_t l = lcp_direct(ks, pa, pb, depth);
+    lcp_out = l;
+    const uint64_t n = ks.pt.n;
+    if (pa + l >= n || pb + l >= n) return pa > pb;  // one suffix is a prefix of the other: the shorter one first
+    return sym_at(ks.pt, pa + l) < sym_at(ks.pt, pb + l);
+}
+__global__ void __launch_bounds__(kBlock) finish_small_groups_kernel(KeySpec ks, uint64_t m, uint64_t depth,
+                                                                     const uint32_t* __restrict__ seg,
+                                                                     const uint32_t* __restrict__ slot,
+                                                                     const pos_t* __restrict__ pos, pos_t* __restrict__ sa,
+                                                                     uint32_t* __restrict__ lcp, uint8_t* __restrict__ is_large,
+                                                                     unsigned long long* __restrict__ large_elems) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
+        const uint32_t g = seg[a];
+        if (a > 0 && seg[a - 1] == g) continue;
+        int len = 1;
+        while (len <= kSmallSeg && a + len < m && seg[a + len] == g) len++;
+        if (len > kSmallSeg) {
+            is_large[g] = 1;
+            atomicAdd(large_elems, 1ull);
+            continue;
+        }
+        pos_t p[kSmallSeg];
+#pragma unroll
+        for (int i = 0; i < kSmallSeg; i++) p[i] = i < len ? pos[a + i] : (pos_t)0;
+        // insertion sort by direct comparison (len <= 8)
+        for (int i = 1; i < len; i++) {
+            const pos_t x = p[i];
+            int j = i;
+            uint64_t l;
+            while (j > 0 && suffix_less(ks, x, p[j - 1], depth, l)) {
+                p[j] = p[j - 1];
+                j--;
+            }
+            p[j] = x;
+        }
+        sa[slot[a]] = p[0];
+        for (int i = 1; i < len; i++) {
+            uint64_t l;
+            suffix_less(ks, p[i - 1], p[i], depth, l);
+            sa[slot[a + i]] = p[i];
+            lcp[slot[a + i]] = (uint32_t)l;
+        }
+    }
+}
+// the members of the groups finish_small_groups_kernel left over, with new group numbers
+struct LeftoverOut {
+    const uint32_t* slot;
+    const pos_t* pos;
+    uint32_t* new_slot;
+    pos_t* new_pos;
+    uint32_t* new_seg;
+    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+        if (val & 1ull) {
+            const uint32_t b = (uint32_t)incl - 1;
+            new_slot[b] = slot[a];
+            new_pos[b] = pos[a];
+            new_seg[b] = (uint32_t)(incl >> 32) - 1;
+        }
+    }
+};
+
 // elements of the flagged groups, in order
 struct LargeIn {
     const uint32_t* seg;
