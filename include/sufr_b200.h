@@ -161,6 +161,26 @@ typedef struct SufrB200VerifyReport {
 int sufr_b200_verify(SufrB200Ctx* ctx, const SufrB200Args* args, const SufrB200Result* result, int has_prev,
                      uint64_t prev_last_suffix, SufrB200VerifyReport* out);
 
+/* -- the consumer of the LCP array: LCP-subsampled suffix array + batched search over a
+ *    device-resident index.  An index borrows text / SA / LCP of a DEVICE result, which must outlive it.
+ *      subsample  SufrFile::subsample_suffix_array (sufr_file.rs:429-456): the entries with lcp < max_query_len and
+ *                 their ranks ("compressed" in-memory suffix array)
+ *      search     SufrSearch::search (sufr_search.rs:104-350) for a batch of queries, one GPU thread per query:
+ *                 queries = concatenated bytes, offsets[num_queries + 1]; has/max_query_len = the run-time `-m`;
+ *                 use_subsample != 0 searches the subsampled array and maps the hits back through the ranks.
+ *                 rank_begin / rank_end (host, num_queries each) = half-open rank range in the full suffix array
+ *                 (SearchResultLocations::ranks), both UINT64_MAX when the query does not occur; count = end - begin.
+ *      suffixes   SA[rank_begin .. rank_begin + count) as u64 (what `locate` reports), host output. */
+typedef struct SufrB200Index SufrB200Index;
+int sufr_b200_index_create(SufrB200Ctx* ctx, const SufrB200Args* args, const SufrB200Result* device_result,
+                           SufrB200Index** out);
+int sufr_b200_index_subsample(SufrB200Index* index, uint64_t max_query_len, uint64_t* kept);
+int sufr_b200_index_search(SufrB200Index* index, const uint8_t* queries, const uint64_t* offsets, uint64_t num_queries,
+                           int has_max_query_len, uint64_t max_query_len, int use_subsample, uint64_t* rank_begin,
+                           uint64_t* rank_end);
+int sufr_b200_index_suffixes(SufrB200Index* index, uint64_t rank_begin, uint64_t count, uint64_t* out);
+void sufr_b200_index_free(SufrB200Index* index);
+
 /* -- write: replaces SufrBuilder::write (sufr_builder.rs:817-918), version-6 `.sufr` layout.
  *    Single shard: writes the whole file.  Sharded: every rank calls it with the same path; rank 0
  *    writes header, text and the names tail, every rank pwrites its SA / LCP slice at its offset.

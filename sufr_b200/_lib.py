@@ -116,6 +116,8 @@ ABI_SYMBOLS = [
     "sufr_b200_ctx_create", "sufr_b200_ctx_destroy", "sufr_b200_ctx_reserve", "sufr_b200_ctx_trim",
     "sufr_b200_build", "sufr_b200_result_free", "sufr_b200_patch_seam", "sufr_b200_verify", "sufr_b200_write",
     "sufr_b200_create", "sufr_b200_create_multi",
+    "sufr_b200_index_create", "sufr_b200_index_subsample", "sufr_b200_index_search", "sufr_b200_index_suffixes",
+    "sufr_b200_index_free",
     "sufr_b200_seed_mask", "sufr_b200_find_lcp_full_offset", "sufr_b200_read_sequence_file",
     "sufr_b200_sequences_free", "sufr_b200_synth_dna", "sufr_b200_last_error", "sufr_b200_abi_version",
     "sufr_b200_device_count",
@@ -163,6 +165,17 @@ def lib():
     L.sufr_b200_create.argtypes = [C.POINTER(Args), C.c_int, C.POINTER(Result)]
     L.sufr_b200_create_multi.restype = C.c_int
     L.sufr_b200_create_multi.argtypes = [C.POINTER(Args), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(Result)]
+    L.sufr_b200_index_create.restype = C.c_int
+    L.sufr_b200_index_create.argtypes = [C.c_void_p, C.POINTER(Args), C.POINTER(Result), C.POINTER(C.c_void_p)]
+    L.sufr_b200_index_subsample.restype = C.c_int
+    L.sufr_b200_index_subsample.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.sufr_b200_index_search.restype = C.c_int
+    L.sufr_b200_index_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
+                                         C.c_void_p, C.c_void_p]
+    L.sufr_b200_index_suffixes.restype = C.c_int
+    L.sufr_b200_index_suffixes.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.sufr_b200_index_free.restype = None
+    L.sufr_b200_index_free.argtypes = [C.c_void_p]
     L.sufr_b200_seed_mask.restype = C.c_int64
     L.sufr_b200_seed_mask.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sufr_b200_find_lcp_full_offset.restype = C.c_uint64

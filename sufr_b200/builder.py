@@ -332,6 +332,85 @@ def build(args: SufrBuilderArgs, *, index_bits: int = 0, ctx: Optional[Context] 
     return BuildResult(ctx, cargs, res)
 
 
+class SufrIndex:
+    """Device-resident index over a DEVICE build result: the read side that consumes the LCP array
+    (``SufrFile::subsample_suffix_array`` sufr_file.rs:429-456, ``suffix_search`` :777-836, ``locate`` :1132-1169,
+    ``SufrSearch`` sufr_search.rs:104-350).  ``count`` / ``locate`` take a batch of queries; one GPU thread each."""
+
+    def __init__(self, result: "BuildResult", args: SufrBuilderArgs):
+        self._res, self._args = result, args
+        self._h = C.c_void_p()
+        _check(_lib.lib().sufr_b200_index_create(result._ctx.handle, C.byref(result._cargs.c), C.byref(result.c),
+                                                 C.byref(self._h)))
+        self._sub_mql = None
+        if args.seed_mask is not None:
+            self._built = SeedMask.new(args.seed_mask).weight        # sufr_file.rs:528
+        else:
+            self._built = args.max_query_len or result.text_len       # sufr_file.rs:521-527
+
+    def close(self):
+        if self._h:
+            _lib.lib().sufr_b200_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def subsample(self, max_query_len: int) -> int:
+        kept = C.c_uint64()
+        _check(_lib.lib().sufr_b200_index_subsample(self._h, max_query_len, C.byref(kept)))
+        self._sub_mql = max_query_len
+        return int(kept.value)
+
+    def search(self, queries: Sequence[str], max_query_len: Optional[int] = None, low_memory: bool = False):
+        """SufrFile::suffix_search: per query the half-open rank range in the full suffix array, or None.
+        low_memory=False mirrors set_suffix_array_mem (sufr_file.rs:514-560): when the effective max_query_len is
+        shorter than what the index was built with, the LCP-subsampled array is searched."""
+        qs = [q.encode() if isinstance(q, str) else bytes(q) for q in queries]
+        offs = np.zeros(len(qs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(q) for q in qs])
+        blob = np.frombuffer(b"".join(qs) or b"\0", dtype=np.uint8)
+        use_sub = 0
+        if not low_memory:
+            eff = min(max_query_len, self._built) if max_query_len else self._built
+            if eff != self._built:
+                if self._sub_mql != eff:
+                    self.subsample(eff)
+                use_sub = 1
+        b = np.zeros(max(1, len(qs)), dtype=np.uint64)
+        e = np.zeros(max(1, len(qs)), dtype=np.uint64)
+        _check(_lib.lib().sufr_b200_index_search(self._h, blob.ctypes.data, offs.ctypes.data, len(qs),
+                                                 int(max_query_len is not None), int(max_query_len or 0), use_sub,
+                                                 b.ctypes.data, e.ctypes.data))
+        none = np.uint64(0xFFFFFFFFFFFFFFFF)
+        return [None if b[i] == none else (int(b[i]), int(e[i])) for i in range(len(qs))]
+
+    def count(self, queries, max_query_len=None, low_memory=False) -> List[int]:
+        return [0 if r is None else r[1] - r[0] for r in self.search(queries, max_query_len, low_memory)]
+
+    def suffixes(self, rank_begin: int, count: int) -> np.ndarray:
+        out = np.zeros(max(1, count), dtype=np.uint64)
+        _check(_lib.lib().sufr_b200_index_suffixes(self._h, rank_begin, count, out.ctypes.data))
+        return out[:count]
+
+    def locate(self, queries, max_query_len=None, low_memory=False):
+        """SufrFile::locate: per query a list of (rank, suffix, sequence_name, sequence_position) in rank order."""
+        import bisect
+        starts, names = list(self._args.sequence_starts), list(self._args.sequence_names)
+        out = []
+        for r in self.search(queries, max_query_len, low_memory):
+            hits = []
+            if r is not None:
+                for k, suf in enumerate(self.suffixes(r[0], r[1] - r[0]).tolist()):
+                    i = bisect.bisect_right(starts, suf) - 1
+                    hits.append((r[0] + k, suf, names[i], suf - starts[i]))
+            out.append(hits)
+        return out
+
+
 def create_multi(args: SufrBuilderArgs, devices: Sequence[int], index_bits: int = 0) -> dict:
     """``sufr::create`` on several GPUs of one box in one call (sufr_b200_create_multi): builds and writes
     ``args.path``; returns the counts and timings of the whole build."""

@@ -37,6 +37,7 @@
 #include "pool.hpp"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "search.cuh"
 #include "verify.cuh"
 
 namespace sufr {
@@ -745,6 +746,157 @@ int sufr_b200_verify(SufrB200Ctx* c, const SufrB200Args* args, const SufrB200Res
         out->deferred_pairs = rep.deferred;
         out->method = (uint32_t)method;
         out->ms = timer.ms(t0, t1);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// LCP-subsampled suffix array + batched search (search.cuh)
+struct SufrB200Index {
+    Ctx* ctx = nullptr;
+    const uint8_t* text = nullptr;
+    const void* sa = nullptr;
+    const void* lcp = nullptr;
+    uint64_t n = 0, s = 0;
+    int wide = 0;
+    bool is_mask = false;
+    uint64_t build_mql = 0;
+    uint32_t weight = 0, mask_len = 0;
+    DevBuf<uint32_t> maskpos;
+    DevBuf<unsigned char> sub_sa, sub_rank;
+    uint64_t sub_len = 0;
+    bool has_sub = false;
+};
+
+int sufr_b200_index_create(SufrB200Ctx* c, const SufrB200Args* args, const SufrB200Result* r, SufrB200Index** out) {
+    return guarded([&] {
+        Ctx* ctx = reinterpret_cast<Ctx*>(c);
+        if (!ctx || !args || !r || !out) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (r->memory != SUFR_B200_MEM_DEVICE || !r->text)
+            throw Error(SUFR_B200_ERR_ARGUMENT, "sufr_b200_index_create needs a device result (with its transformed text)");
+        if (args->world_size > 1) throw Error(SUFR_B200_ERR_ARGUMENT, "an index needs the whole suffix array (world_size <= 1)");
+        auto idx = std::make_unique<SufrB200Index>();
+        idx->ctx = ctx;
+        idx->text = r->text;
+        idx->sa = r->sa;
+        idx->lcp = r->lcp;
+        idx->n = r->text_len;
+        idx->s = r->num_suffixes;
+        idx->wide = r->index_bits == 64;
+        SeedMaskInfo mask;
+        if (args->seed_mask && parse_seed_mask(args->seed_mask, mask)) {
+            std::lock_guard<std::mutex> lock(ctx->mu);
+            SUFR_CUDA_CHECK(cudaSetDevice(ctx->device));
+            idx->is_mask = true;
+            idx->weight = (uint32_t)mask.weight;
+            idx->mask_len = (uint32_t)mask.bytes.size();
+            std::vector<uint32_t> mp(mask.positions.begin(), mask.positions.end());
+            idx->maskpos = DevBuf<uint32_t>(ctx->pool, mp.size());
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(idx->maskpos.get(), mp.data(), mp.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        } else {
+            idx->build_mql = args->has_max_query_len ? args->max_query_len : 0;
+        }
+        *out = idx.release();
+    });
+}
+
+void sufr_b200_index_free(SufrB200Index* idx) {
+    if (!idx) return;
+    {
+        std::lock_guard<std::mutex> lock(idx->ctx->mu);
+        idx->maskpos.reset();
+        idx->sub_sa.reset();
+        idx->sub_rank.reset();
+    }
+    delete idx;
+}
+
+int sufr_b200_index_subsample(SufrB200Index* idx, uint64_t max_query_len, uint64_t* kept) {
+    return guarded([&] {
+        if (!idx) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        Ctx& ctx = *idx->ctx;
+        std::lock_guard<std::mutex> lock(ctx.mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx.device));
+        idx->sub_sa.reset();
+        idx->sub_rank.reset();
+        idx->has_sub = false;
+        idx->sub_len = 0;
+        const size_t w = idx->wide ? 8 : 4;
+        search::SubsampleIn in{idx->lcp, idx->wide, max_query_len};
+        DevBuf<uint32_t> partials(ctx.pool, scan::partials_count(idx->s));
+        uint32_t total = 0;
+        if (idx->s) {
+            scan::scan_reduce(idx->s, in, scan::SumU32{}, partials.get(), ctx.stream);
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(&total, partials.get() + div_up(idx->s, scan::CHUNK), 4, cudaMemcpyDeviceToHost, ctx.stream));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        }
+        idx->sub_sa = DevBuf<unsigned char>(ctx.pool, (size_t)total * w + 8);
+        idx->sub_rank = DevBuf<unsigned char>(ctx.pool, (size_t)total * w + 8);
+        if (idx->s) {
+            scan::scan_apply(idx->s, in, scan::SumU32{}, search::SubsampleOut{idx->sa, idx->wide, idx->sub_sa.get(), idx->sub_rank.get()},
+                             partials.get(), ctx.stream);
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        }
+        idx->sub_len = total;
+        idx->has_sub = true;
+        if (kept) *kept = total;
+    });
+}
+
+int sufr_b200_index_search(SufrB200Index* idx, const uint8_t* queries, const uint64_t* offsets, uint64_t nq, int has_mql,
+                           uint64_t mql, int use_subsample, uint64_t* rank_begin, uint64_t* rank_end) {
+    return guarded([&] {
+        if (!idx || !offsets || !rank_begin || !rank_end || (nq && !queries && offsets[nq])) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (use_subsample && !idx->has_sub) throw Error(SUFR_B200_ERR_ARGUMENT, "sufr_b200_index_subsample has not been called");
+        if (nq == 0) return;
+        Ctx& ctx = *idx->ctx;
+        std::lock_guard<std::mutex> lock(ctx.mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx.device));
+        const uint64_t bytes = offsets[nq];
+        DevBuf<uint8_t> d_q(ctx.pool, bytes + 8);
+        DevBuf<uint64_t> d_off(ctx.pool, nq + 1);
+        DevBuf<unsigned long long> d_b(ctx.pool, nq), d_e(ctx.pool, nq);
+        if (bytes) SUFR_CUDA_CHECK(cudaMemcpyAsync(d_q.get(), queries, bytes, cudaMemcpyHostToDevice, ctx.stream));
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(d_off.get(), offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, ctx.stream));
+        search::Params P{};
+        P.text = idx->text;
+        P.n = idx->n;
+        P.sa = use_subsample ? (const void*)idx->sub_sa.get() : idx->sa;
+        P.rank = use_subsample ? (const void*)idx->sub_rank.get() : nullptr;
+        P.len = use_subsample ? idx->sub_len : idx->s;
+        P.wide = idx->wide;
+        P.is_mask = idx->is_mask;
+        P.build_mql = idx->build_mql;
+        P.has_run_mql = has_mql ? 1 : 0;
+        P.run_mql = mql;
+        P.mask_pos = idx->maskpos.get();
+        P.weight = idx->weight;
+        P.mask_len = idx->mask_len;
+        search::search_kernel<<<(unsigned)div_up(nq, 128), 128, 0, ctx.stream>>>(P, d_q.get(), d_off.get(), nq, d_b.get(), d_e.get());
+        SUFR_KERNEL_CHECK();
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(rank_begin, d_b.get(), nq * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        SUFR_CUDA_CHECK(cudaMemcpyAsync(rank_end, d_e.get(), nq * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    });
+}
+
+int sufr_b200_index_suffixes(SufrB200Index* idx, uint64_t rank_begin, uint64_t count, uint64_t* out) {
+    return guarded([&] {
+        if (!idx || (count && !out)) throw Error(SUFR_B200_ERR_ARGUMENT, "NULL argument");
+        if (rank_begin > idx->s || count > idx->s - rank_begin) throw Error(SUFR_B200_ERR_ARGUMENT, "rank range out of bounds");
+        if (count == 0) return;
+        Ctx& ctx = *idx->ctx;
+        std::lock_guard<std::mutex> lock(ctx.mu);
+        SUFR_CUDA_CHECK(cudaSetDevice(ctx.device));
+        if (idx->wide) {
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(out, (const uint64_t*)idx->sa + rank_begin, count * 8, cudaMemcpyDeviceToHost, ctx.stream));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        } else {
+            std::vector<uint32_t> tmp(count);
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), (const uint32_t*)idx->sa + rank_begin, count * 4, cudaMemcpyDeviceToHost, ctx.stream));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+            for (uint64_t i = 0; i < count; i++) out[i] = tmp[i];
+        }
     });
 }
 
