@@ -365,13 +365,13 @@ def main():
 
 
 TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on the "
-                  "200 Mbp workload (profiles/r1_v7_downsweep_raw.csv: 2.781 GB + 2.686 GB for 4.800 GB "
-                  "algorithmic), scaled to this launch's element count")
+                  "1.0 Gbp workload (profiles/r2_v12_ncu_full_1000Mbp_build_raw.csv: 12.557 GB + 12.451 GB for "
+                  "24.000 GB algorithmic), scaled to this launch's element count")
 
 
 def traffic_estimate(algorithmic_bytes):
     """DRAM bytes per launch of the dominant kernel (see TRAFFIC_SOURCE)."""
-    return algorithmic_bytes * (2.781094 + 2.685538) / 4.800000576
+    return algorithmic_bytes * (12.557185 + 12.451262) / 24.000000
 
 
 FULL_SIZES = {"config1": 10_000_000, "config2b": 3_100_000_000, "config3": 1_000_000_000,

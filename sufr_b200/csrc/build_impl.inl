@@ -113,6 +113,7 @@ class Build {
     void refine(DevBuf<uint64_t>& keys_sorted);
     void doubling(DevBuf<uint32_t>& slot, DevBuf<pos_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
                   uint64_t h);
+    void isa_init(uint32_t* isa);
     void n_run_rule();
     void apply_filter();
     void segmented_sort_u64key(DevBuf<uint64_t>& ck, DevBuf<pos_t>& pos, uint64_t m, int key_bits);
@@ -775,6 +776,54 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     }
 }
 
+// isa[sa[j]] = j for the whole suffix array.  Large arrays go through one or two radix passes on the top bits of the
+// position (slices of 2^29 ranks, so the temporaries stay at 8 GB) and a windowed scatter; see isa_apply_kernel.
+void Build::isa_init(uint32_t* isa) {
+    // SUFR_B200_DEBUG_BUCKET_ISA = 1 | 2 takes the bucketed route (with that many passes) on small texts too: tests
+    const char* force = getenv("SUFR_B200_DEBUG_BUCKET_ISA");
+    const bool direct = sizeof(pos_t) != 4 || n < 4096 || (!force && n < (1ull << 26)) || getenv("SUFR_B200_DEBUG_DIRECT_ISA");
+    if (direct) {
+        isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa);
+        SUFR_KERNEL_CHECK();
+        launched();
+        return;
+    }
+    if constexpr (sizeof(pos_t) == 4) {
+        const int nbits = bits_for(n - 1);
+        // one pass leaves 256 buckets of the array; a second one (3 more bits) when a bucket would not sit well inside the L2
+        const bool two = force ? force[0] == '2' : ((4ull << nbits) >> 8) > (40ull << 20);
+        const uint64_t slice = force ? 10000 : 1ull << 29;
+        const uint64_t cap = std::min<uint64_t>(slice, n);
+        auto kb = dalloc<uint32_t>(cap), va = dalloc<uint32_t>(cap), vb = dalloc<uint32_t>(cap);
+        DevBuf<uint32_t> ka;
+        if (two) ka = dalloc<uint32_t>(cap);
+        if (!d_counts) d_counts = dalloc<uint32_t>(rsort::counts_words());
+        for (uint64_t base = 0; base < n; base += slice) {
+            const uint64_t cnt = std::min<uint64_t>(slice, n - base);
+            uint32_t* sa_slice = reinterpret_cast<uint32_t*>(d_sa.get()) + base;  // read only: each call below is ONE pass
+            iota_kernel<<<grid_for(cnt, 4), kBlock, 0, st()>>>(va.get(), cnt, (uint32_t)base);
+            SUFR_KERNEL_CHECK();
+            const uint32_t *rk, *rv;
+            if (two) {
+                rsort::sort_pairs<uint32_t, uint32_t>(sa_slice, kb.get(), va.get(), vb.get(), cnt, nbits - 11, nbits - 8,
+                                                      d_counts.get(), st(), &ctx.launches);
+                rsort::sort_pairs<uint32_t, uint32_t>(kb.get(), ka.get(), vb.get(), va.get(), cnt, nbits - 8, nbits,
+                                                      d_counts.get(), st(), &ctx.launches);
+                rk = ka.get();
+                rv = va.get();
+            } else {
+                rsort::sort_pairs<uint32_t, uint32_t>(sa_slice, kb.get(), va.get(), vb.get(), cnt, nbits - 8, nbits,
+                                                      d_counts.get(), st(), &ctx.launches);
+                rk = kb.get();
+                rv = vb.get();
+            }
+            isa_apply_kernel<<<grid_for(cnt, 4), kBlock, 0, st()>>>(cnt, rk, rv, isa);
+            SUFR_KERNEL_CHECK();
+            launched(2);
+        }
+    }
+}
+
 // Prefix doubling on the still-unresolved groups (Larsson-Sadakane style: only active groups are sorted).
 // Needs the rank of EVERY text position, hence only valid when all positions were sorted on this rank.
 void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<pos_t>& pos, DevBuf<uint32_t>& seg, uint64_t m, uint64_t nseg,
@@ -782,9 +831,7 @@ void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<pos_t>& pos, DevBuf<uint32_t
     if (!full_set_) throw NeedFullSort{};
     d_isa = dalloc<uint32_t>(n);
     uint32_t* const isa_ptr = d_isa.get();
-    isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa_ptr);
-    SUFR_KERNEL_CHECK();
-    launched();
+    isa_init(isa_ptr);
     scan_total(m, GroupStartIn{seg.get()}, scan::MaxU32{}, GroupRankOut{slot.get(), pos.get(), isa_ptr});
     const bool log_rounds = getenv("SUFR_B200_LOG_ROUNDS") != nullptr;
     while (m > 0) {

@@ -1139,6 +1139,18 @@ __global__ void __launch_bounds__(kBlock) isa_init_kernel(uint64_t n, const pos_
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) isa[sa[j]] = (uint32_t)j;
 }
+// The same through records (position, rank) that a radix pass has ordered by the top bits of the position: all blocks
+// walk the records together, so the 4-byte stores of a moment fall into a window of the array that the L2 holds and
+// leave it as whole sectors (a direct scatter costs a 32-byte read and a 32-byte write of DRAM per rank).
+__global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* __restrict__ out, uint64_t count, uint32_t base) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) out[j] = base + (uint32_t)j;
+}
+__global__ void __launch_bounds__(kBlock) isa_apply_kernel(uint64_t count, const uint32_t* __restrict__ p,
+                                                           const uint32_t* __restrict__ rank, uint32_t* __restrict__ isa) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) isa[p[j]] = rank[j];
+}
 
 // rank of an active element = SA slot of the first element of its group
 struct GroupStartIn {
@@ -1181,7 +1193,8 @@ struct DoublingRankOut {
     uint32_t mark;  // kLcpLowerBound | min(h, 2^31 - 1)
     int rank_bits;
     __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const {
-        isa[pos[a]] = slot[first];
+        // the first subgroup of a group keeps the group's rank (the slot of its first element): nothing to write
+        if (first > 0 && (ck[first] >> rank_bits) == (ck[first - 1] >> rank_bits)) isa[pos[a]] = slot[first];
         if (a > 0 && ck[a] != ck[a - 1] && (ck[a] >> rank_bits) == (ck[a - 1] >> rank_bits)) lcp[slot[a]] = mark;
     }
 };

@@ -3,7 +3,7 @@
 // Used for every order-preserving compaction on the path (active-group compaction, shard
 // selection, suffix filter) and for the max / segmented-min scans of the refinement stages.
 // Three launches, two coalesced reads of the input functor, no inter-block dependencies
-// (so no forward-progress assumptions).
+// (so no forward-progress assumptions).  The operator must be associative; it need not commute.
 #pragma once
 #include "common.cuh"
 
@@ -74,22 +74,43 @@ __device__ __forceinline__ typename Op::T block_inclusive(typename Op::T v, Op o
     return incl;
 }
 
-// Each thread owns ITEMS consecutive elements (thread-local sequential scan), so a chunk needs ONE
-// block-level scan instead of one per row of 256 elements.
+// Layout of a chunk: warp w owns the 32 * ITEMS consecutive elements [w * 32 * ITEMS, ...), as ITEMS rows of 32; lane l
+// reads element row * 32 + l, so every access the input / output functors make with consecutive indices is coalesced
+// (a thread that owned ITEMS consecutive elements would stride its warp's loads by ITEMS elements).
+// Scan order inside the warp is row-major: a warp scan per row, a running prefix over the rows.
+template <typename Op>
+__device__ __forceinline__ typename Op::T warp_reduce_in_order(typename Op::T v, Op op) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        typename Op::T o = __shfl_down_sync(0xffffffffu, v, off);
+        v = op(v, o);  // lane 0 ends with e0 (+) e1 (+) ... (+) e31; the other lanes are not used
+    }
+    return v;
+}
+
 template <typename Op, typename In>
 __global__ void __launch_bounds__(BLOCK) reduce_kernel(uint64_t n, In in, Op op, typename Op::T* partials) {
     using T = typename Op::T;
     __shared__ T smem[BLOCK / 32];
-    const uint64_t i0 = (uint64_t)blockIdx.x * CHUNK + (uint64_t)threadIdx.x * ITEMS;
-    T acc = Op::identity();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t w0 = (uint64_t)blockIdx.x * CHUNK + (uint64_t)warp * (32 * ITEMS) + lane;
+    T v[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        uint64_t i = i0 + k;
-        if (i < n) acc = op(acc, in(i));
+        const uint64_t i = w0 + (uint64_t)k * 32;
+        v[k] = i < n ? in(i) : Op::identity();
     }
-    T total;
-    block_inclusive(acc, op, smem, total);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+    T acc = Op::identity();
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) acc = op(acc, warp_reduce_in_order(v[k], op));  // meaningful in lane 0
+    if (lane == 0) smem[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T total = smem[0];
+#pragma unroll
+        for (int w = 1; w < BLOCK / 32; w++) total = op(total, smem[w]);
+        partials[blockIdx.x] = total;
+    }
 }
 
 // Single block: exclusive scan of the per-chunk partials, in place. `total_out` receives the grand total.
@@ -126,30 +147,34 @@ __global__ void __launch_bounds__(BLOCK) apply_kernel(uint64_t n, In in, Op op, 
                                                       Out out) {
     using T = typename Op::T;
     __shared__ T smem[BLOCK / 32];
-    const uint64_t i0 = (uint64_t)blockIdx.x * CHUNK + (uint64_t)threadIdx.x * ITEMS;
-    T v[ITEMS];
-    T acc = Op::identity();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t w0 = (uint64_t)blockIdx.x * CHUNK + (uint64_t)warp * (32 * ITEMS) + lane;
+    T v[ITEMS], s[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        uint64_t i = i0 + k;
+        const uint64_t i = w0 + (uint64_t)k * 32;
         v[k] = i < n ? in(i) : Op::identity();
-        acc = op(acc, v[k]);
     }
-    T total;
-    T incl = block_inclusive(acc, op, smem, total);
-    // exclusive prefix of this thread = carry (+) inclusive of the previous thread
-    T prev = __shfl_up_sync(0xffffffffu, incl, 1);
-    __shared__ T last_of_warp[BLOCK / 32];
-    if ((threadIdx.x & 31) == 31) last_of_warp[threadIdx.x >> 5] = incl;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) s[k] = warp_inclusive(v[k], op, lane);
+    // running prefix over the rows of this warp (the row totals are warp-uniform)
+    T wtotal = Op::identity();
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const T row = __shfl_sync(0xffffffffu, s[k], 31);
+        s[k] = op(wtotal, s[k]);
+        wtotal = op(wtotal, row);
+    }
+    if (lane == 0) smem[warp] = wtotal;
     __syncthreads();
     T prefix = partials[blockIdx.x];
-    if (threadIdx.x != 0) prefix = op(prefix, (threadIdx.x & 31) == 0 ? last_of_warp[(threadIdx.x >> 5) - 1] : prev);
-    T run = prefix;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++)
+        if (w < warp) prefix = op(prefix, smem[w]);
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        uint64_t i = i0 + k;
-        run = op(run, v[k]);
-        if (i < n) out(i, v[k], run);
+        const uint64_t i = w0 + (uint64_t)k * 32;
+        if (i < n) out(i, v[k], op(prefix, s[k]));
     }
 }
 

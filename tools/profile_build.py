@@ -2,7 +2,7 @@
 """One build of the headline workload inside a cudaProfilerStart/Stop range (after two warm-up builds), for
 
     ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:<kernels> \
-        -o gpurun_out/prof python tools/profile_build.py [bases] [index_bits]
+        -o gpurun_out/prof python tools/profile_build.py [bases] [index_bits] [rank world_size]
 """
 import sys
 from pathlib import Path
@@ -18,6 +18,7 @@ from sufr_b200 import _lib  # noqa: E402
 
 bases = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
 bits = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+shard = dict(rank=int(sys.argv[3]), world_size=int(sys.argv[4])) if len(sys.argv) > 4 else {}
 text_len, starts = bench.record_layout(bases)
 ctx = S.Context(0)
 d_text = torch.empty(text_len, dtype=torch.uint8, device="cuda")
@@ -28,7 +29,7 @@ for i in range(3):
     if i == 2:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-    r = S.build(bargs, index_bits=bits, ctx=ctx, result_memory=S.MEM_DEVICE, device_text=(d_text.data_ptr(), text_len))
+    r = S.build(bargs, index_bits=bits, ctx=ctx, result_memory=S.MEM_DEVICE, device_text=(d_text.data_ptr(), text_len), **shard)
     torch.cuda.synchronize()
     if i == 2:
         torch.cuda.profiler.stop()

@@ -21,8 +21,13 @@ t = torch.frombuffer(bytearray(w.text), dtype=torch.uint8).cuda()
 args = S.SufrBuilderArgs(text=b"", sequence_starts=w.sequence_starts, sequence_names=w.sequence_names, **w.flags)
 for i in range(2):
     print(f"--- build {i}", file=sys.stderr, flush=True)
+    if i == 1 and os.environ.get("SUFR_PROFILE"):  # ncu --profile-from-start off: the second build only
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     t0 = time.time()
     r = S.build(args, index_bits=w.index_bits, result_memory=S.MEM_DEVICE, device_text=(t.data_ptr(), t.numel()))
     torch.cuda.synchronize()
+    if i == 1 and os.environ.get("SUFR_PROFILE"):
+        torch.cuda.profiler.stop()
     print(f"--- {name}: {r.num_suffixes} suffixes, wall {time.time() - t0:.3f} s, phases {r.timings}", file=sys.stderr, flush=True)
     r.free()

@@ -36,7 +36,11 @@ __device__ __host__ inline uint64_t mix64(uint64_t z) {
 __global__ void init_kernel(uint64_t* k, uint32_t* v, uint64_t n, int skew) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t z = mix64((i + 1) * 0x9E3779B97F4A7C15ull);
-        if (skew) z &= 0x0303FF0FFFFFFFFFull;  // few distinct digits
+        if (skew == 1) z &= 0x0303FF0FFFFFFFFFull;  // few distinct digits
+        if (skew >= 2) {  // every sorted digit takes one of (1 << (skew - 2)) values: 2 -> all records in one bin
+            const uint64_t keep = (1ull << (skew - 2)) - 1;
+            z &= ~0x00FFFFFF00000000ull | (keep << 32) | (keep << 40) | (keep << 48);
+        }
         k[i] = z;
         v[i] = (uint32_t)i;
     }
@@ -180,6 +184,41 @@ void run_matrix(const char* name, Bufs& B, int begin_bit, int end_bit) {
     fflush(stdout);
 }
 
+// How much of the scatter pass is the DRAM locality of its writes?  The same kernel on keys whose digits take 1, 4, 16,
+// 64 or 256 values: the instruction count per record is the same, only the length of the per-digit output runs changes.
+template <int BLOCK, int IPT, int CTAS, int MODE>
+void run_locality(Bufs& B) {
+    using Cfg = osort::PassConfig<uint64_t, uint32_t, BLOCK, IPT, MODE>;
+    auto kern = osort::onesweep_kernel<uint64_t, uint32_t, BLOCK, IPT, CTAS, MODE, 0>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::dyn_smem));
+    const uint64_t tiles = (B.n + Cfg::TILE - 1) / Cfg::TILE;
+    uint32_t grid = 148 * CTAS;
+    const uint32_t tpb = (uint32_t)((tiles + grid - 1) / grid);
+    grid = (uint32_t)((tiles + tpb - 1) / tpb);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int bits : {0, 2, 4, 6, 8}) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            init_kernel<<<148 * 8, 256>>>(B.ka, B.va, B.n, bits == 8 ? 0 : 2 + bits);
+            rsort_r1::upsweep_kernel<uint64_t, Cfg::TILE / 256><<<grid, 256>>>(B.ka, B.n, 32, 255u, B.counts, tpb);
+            rsort_r1::scan_counts_kernel<<<1, 1024>>>(B.counts, 256u * grid);
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(e0));
+            kern<<<grid, BLOCK, Cfg::dyn_smem>>>(B.ka, B.kb, B.va, B.vb, B.n, 32, 255u, nullptr, nullptr, 0, 0u, nullptr, nullptr, 0u,
+                                                 B.counts, tpb);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            CK(cudaGetLastError());
+            best = std::min(best, elapsed(e0, e1));
+        }
+        printf("locality <%d,%d,%d>: %3d distinct digits -> scatter pass %7.3f ms  %6.0f GB/s\n", BLOCK, IPT, CTAS, 1 << bits, best,
+               (double)B.n * 24 / (best * 1e-3) / 1e9);
+    }
+    fflush(stdout);
+}
+
 template <int BLOCK, int IPT, int CTAS, int MODE, int LB>
 bool small_check(const char* name, int skew) {
     using Cfg = osort::PassConfig<uint64_t, uint32_t, BLOCK, IPT, MODE>;
@@ -305,6 +344,11 @@ int main(int argc, char** argv) {
         printf("%-34s 3 x (count + scan + scatter), 512 threads x 16, 1 CTA/SM     | total %7.3f ms | %6.0f GB/s per pass incl. count%s\n",
                "round-2 rsort::sort_pairs", best, (double)n * 24 * 3 / (best * 1e-3) / 1e9, bad ? "  !! DIFFERS" : "");
         fflush(stdout);
+    }
+    if (getenv("SORT_BENCH_LOCALITY")) {
+        run_locality<512, 16, 1, osort::kRegsBulk>(B);
+        run_locality<256, 16, 2, osort::kRegsBulk>(B);
+        return 0;
     }
     MAT(256, 16, 2, kRegsBulk);
     MAT(512, 8, 2, kRegsBulk);
