@@ -817,7 +817,9 @@ void Build::isa_init(uint32_t* isa) {
                 rk = kb.get();
                 rv = vb.get();
             }
-            isa_apply_kernel<<<grid_for(cnt, 4), kBlock, 0, st()>>>(cnt, rk, rv, isa);
+            // every block resident at once (8 x 256 threads per SM): the grid sweeps the records ONCE, front to back
+            const uint32_t resident = (uint32_t)std::min<uint64_t>(div_up(cnt, kBlock), (uint64_t)num_sms() * 8);
+            isa_apply_kernel<<<resident, kBlock, 0, st()>>>(cnt, rk, rv, isa);
             SUFR_KERNEL_CHECK();
             launched(2);
         }

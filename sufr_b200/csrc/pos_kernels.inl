@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kBlock) count_indexed_kernel(const uint8_t* __
 // Selection of the suffixes this build sorts: the suffix filter (sufr_builder.rs:446-449) applied up front,
 // and / or the key range [lo, hi) of this rank's shard (multi-GPU).  Order-preserving compaction.
 struct SelectIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     KeySpec ks;
     uint64_t n;
     int descending;
@@ -804,12 +805,14 @@ __global__ void __launch_bounds__(kBlock) lcp_fixup_kernel(KeySpec ks, uint64_t 
 
 // Group structure of the fast path after round 0, read off the LCP marks: record j continues the group of record
 // j-1 iff lcp[j] == kLcpPending; it is unresolved iff it continues a group or its successor does.
-struct LcpSegIn {  // segment ids of the slot-sorted unresolved list
+struct LcpSegIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes  // segment ids of the slot-sorted unresolved list
     const uint32_t* lcp;
     const uint32_t* slot;
     __device__ uint32_t operator()(uint64_t a) const { return lcp[slot[a]] != kLcpPending ? 1u : 0u; }
 };
-struct LcpActiveIn {  // dense variant: order-preserving compaction of all unresolved records
+struct LcpActiveIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes  // dense variant: order-preserving compaction of all unresolved records
     const uint32_t* lcp;
     uint64_t m;
     __device__ unsigned long long operator()(uint64_t i) const {
@@ -823,11 +826,12 @@ struct LcpActiveOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    __device__ void operator()(uint64_t i, unsigned long long val, unsigned long long incl) const {
+    __device__ pos_t load(uint64_t i, unsigned long long val, unsigned long long) const { return (val & 1ull) ? pos[i] : (pos_t)0; }
+    __device__ void store(uint64_t i, unsigned long long val, unsigned long long incl, pos_t p) const {
         if (val & 1ull) {
             const uint32_t a = (uint32_t)incl - 1;
             new_slot[a] = (uint32_t)i;
-            new_pos[a] = pos[i];
+            new_pos[a] = p;
             new_seg[a] = (uint32_t)(incl >> 32) - 1;
         }
     }
@@ -867,6 +871,7 @@ __global__ void __launch_bounds__(kBlock) lcp_bounds_direct_kernel(KeySpec ks, u
 // segment ids of the slot-sorted active list: a new segment starts where the key differs from the
 // previous SA slot's key
 struct SparseSegIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     ViewAll v;  // group keys of the sorted array
     const uint32_t* slot;
     __device__ uint32_t operator()(uint64_t a) const {
@@ -883,17 +888,21 @@ struct SparseSegOut {
 // bit 32 = active and first of its group.
 template <typename View>
 struct ActiveIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     View v;
     uint64_t m;
     int final_word;
     int sentinel;  // filtered suffixes ride along with key ~0 (only with packings that leave a low bit unused)
     __device__ unsigned long long operator()(uint64_t i) const {
         if (final_word) return 0;
-        uint64_t ki = v.k(i);
-        if (sentinel && v.raw(i) == ~0ull) return 0;  // never refined
-        bool head = !v.same_seg(i) || v.k(i - 1) != ki;
-        bool next_same = (i + 1 < m) && v.same_seg(i + 1) && v.k(i + 1) == ki;
-        bool active = !head || next_same;
+        // every load is issued unconditionally (clamped indices): a load behind a branch on another load's value
+        // would serialise the memory round trips of a thread's rows
+        const uint64_t ip = i > 0 ? i - 1 : 0, in = i + 1 < m ? i + 1 : i;
+        const uint64_t ki = v.k(i), kp = v.k(ip), kn = v.k(in), raw = v.raw(i);
+        const bool seg_i = v.same_seg(i), seg_n = v.same_seg(in);
+        const bool head = !seg_i | (kp != ki);
+        const bool next_same = (i + 1 < m) & seg_n & (kn == ki);
+        const bool active = (!head | next_same) & !(sentinel && raw == ~0ull);  // sentinel keys are never refined
         return active ? (1ull | ((unsigned long long)head << 32)) : 0ull;
     }
 };
@@ -903,11 +912,17 @@ struct ActiveOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    __device__ void operator()(uint64_t i, unsigned long long val, unsigned long long incl) const {
+    struct Staged { uint32_t slot; pos_t pos; };
+    __device__ Staged load(uint64_t i, unsigned long long val, unsigned long long) const {
+        Staged st{0, 0};
+        if (val & 1ull) { st.slot = v.slot(i); st.pos = v.p(i); }
+        return st;
+    }
+    __device__ void store(uint64_t, unsigned long long val, unsigned long long incl, const Staged& st) const {
         if (val & 1ull) {
             uint32_t a = (uint32_t)incl - 1;
-            new_slot[a] = v.slot(i);
-            new_pos[a] = v.p(i);
+            new_slot[a] = st.slot;
+            new_pos[a] = st.pos;
             new_seg[a] = (uint32_t)(incl >> 32) - 1;
         }
     }
@@ -1037,11 +1052,17 @@ struct LeftoverOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+    struct Staged { uint32_t slot; pos_t pos; };
+    __device__ Staged load(uint64_t a, unsigned long long val, unsigned long long) const {
+        Staged st{0, 0};
+        if (val & 1ull) { st.slot = slot[a]; st.pos = pos[a]; }
+        return st;
+    }
+    __device__ void store(uint64_t, unsigned long long val, unsigned long long incl, const Staged& st) const {
         if (val & 1ull) {
             const uint32_t b = (uint32_t)incl - 1;
-            new_slot[b] = slot[a];
-            new_pos[b] = pos[a];
+            new_slot[b] = st.slot;
+            new_pos[b] = st.pos;
             new_seg[b] = (uint32_t)(incl >> 32) - 1;
         }
     }
@@ -1049,13 +1070,13 @@ struct LeftoverOut {
 
 // elements of the flagged groups, in order
 struct LargeIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const uint32_t* seg;
     const uint8_t* flagged;
     __device__ unsigned long long operator()(uint64_t a) const {
-        uint32_t g = seg[a];
-        if (!flagged[g]) return 0ull;
-        bool head = a == 0 || seg[a - 1] != g;
-        return 1ull | ((unsigned long long)head << 32);
+        const uint32_t g = seg[a], gp = seg[a > 0 ? a - 1 : 0];
+        const bool head = a == 0 || gp != g;
+        return flagged[g] ? (1ull | ((unsigned long long)head << 32)) : 0ull;
     }
 };
 struct LargeOut {
@@ -1065,13 +1086,19 @@ struct LargeOut {
     uint64_t* lkeys;
     uint64_t* segidx;   // sort payload: compact group number << 32 | compact index (positions may need 64 bits)
     pos_t* lpos;        // position of compact element b
-    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+    struct Staged { uint64_t key; pos_t pos; };
+    __device__ Staged load(uint64_t a, unsigned long long val, unsigned long long) const {
+        Staged st{0, 0};
+        if (val & 1ull) { st.key = keys[a]; st.pos = pos[a]; }
+        return st;
+    }
+    __device__ void store(uint64_t a, unsigned long long val, unsigned long long incl, const Staged& st) const {
         if (val & 1ull) {
             uint32_t b = (uint32_t)incl - 1;
             idx[b] = (uint32_t)a;
-            lkeys[b] = keys[a];
+            lkeys[b] = st.key;
             segidx[b] = (((incl >> 32) - 1) << 32) | b;
-            lpos[b] = pos[a];
+            lpos[b] = st.pos;
         }
     }
 };
@@ -1083,12 +1110,18 @@ struct LargeOutRank {
     uint64_t* lck;
     pos_t* lpos;
     int rank_bits;
-    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+    struct Staged { uint64_t key; pos_t pos; };
+    __device__ Staged load(uint64_t a, unsigned long long val, unsigned long long) const {
+        Staged st{0, 0};
+        if (val & 1ull) { st.key = keys[a]; st.pos = pos[a]; }
+        return st;
+    }
+    __device__ void store(uint64_t a, unsigned long long val, unsigned long long incl, const Staged& st) const {
         if (val & 1ull) {
             uint32_t b = (uint32_t)incl - 1;
             idx[b] = (uint32_t)a;
-            lck[b] = (((incl >> 32) - 1) << rank_bits) | (keys[a] & ((1ull << rank_bits) - 1ull));
-            lpos[b] = pos[a];
+            lck[b] = (((incl >> 32) - 1) << rank_bits) | (st.key & ((1ull << rank_bits) - 1ull));
+            lpos[b] = st.pos;
         }
     }
 };
@@ -1154,6 +1187,7 @@ __global__ void __launch_bounds__(kBlock) isa_apply_kernel(uint64_t count, const
 
 // rank of an active element = SA slot of the first element of its group
 struct GroupStartIn {
+    static constexpr bool kLastIndex = true;  // scan.cuh: scanned with warp votes
     const uint32_t* seg;
     __device__ uint32_t operator()(uint64_t a) const { return (a == 0 || seg[a] != seg[a - 1]) ? (uint32_t)a : 0u; }
 };
@@ -1161,7 +1195,9 @@ struct GroupRankOut {
     const uint32_t* slot;
     const pos_t* pos;
     uint32_t* isa;
-    __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const { isa[pos[a]] = slot[first]; }
+    struct Staged { uint32_t rank; pos_t pos; };
+    __device__ Staged load(uint64_t a, uint32_t, uint32_t first) const { return Staged{slot[first], pos[a]}; }
+    __device__ void store(uint64_t, uint32_t, uint32_t, const Staged& st) const { isa[st.pos] = st.rank; }
 };
 
 // composite key (segment << rank_bits | rank of suffix p+h, 0 = beyond the end); rank_bits = bits of n, so that
@@ -1180,6 +1216,7 @@ __global__ void __launch_bounds__(kBlock) doubling_keys_kernel(uint64_t m, uint6
 }
 
 struct DoublingStartIn {
+    static constexpr bool kLastIndex = true;  // scan.cuh: scanned with warp votes
     const uint64_t* ck;
     __device__ uint32_t operator()(uint64_t a) const { return (a == 0 || ck[a] != ck[a - 1]) ? (uint32_t)a : 0u; }
 };
@@ -1192,13 +1229,25 @@ struct DoublingRankOut {
     uint32_t* lcp;
     uint32_t mark;  // kLcpLowerBound | min(h, 2^31 - 1)
     int rank_bits;
-    __device__ void operator()(uint64_t a, uint32_t, uint32_t first) const {
+    struct Staged { uint32_t rank, mslot; pos_t pos; bool write, marked; };
+    __device__ Staged load(uint64_t a, uint32_t, uint32_t first) const {
+        const uint64_t cf = ck[first], cfp = ck[first > 0 ? first - 1 : 0], ca = ck[a], cap = ck[a > 0 ? a - 1 : 0];
+        Staged st;
         // the first subgroup of a group keeps the group's rank (the slot of its first element): nothing to write
-        if (first > 0 && (ck[first] >> rank_bits) == (ck[first - 1] >> rank_bits)) isa[pos[a]] = slot[first];
-        if (a > 0 && ck[a] != ck[a - 1] && (ck[a] >> rank_bits) == (ck[a - 1] >> rank_bits)) lcp[slot[a]] = mark;
+        st.write = first > 0 && (cf >> rank_bits) == (cfp >> rank_bits);
+        st.marked = a > 0 && ca != cap && (ca >> rank_bits) == (cap >> rank_bits);
+        st.rank = slot[first];
+        st.mslot = slot[a];
+        st.pos = pos[a];
+        return st;
+    }
+    __device__ void store(uint64_t, uint32_t, uint32_t, const Staged& st) const {
+        if (st.write) isa[st.pos] = st.rank;
+        if (st.marked) lcp[st.mslot] = mark;
     }
 };
 struct DoublingActiveIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const uint64_t* ck;
     uint64_t m;
     __device__ unsigned long long operator()(uint64_t a) const {
@@ -1215,11 +1264,17 @@ struct DoublingActiveOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    __device__ void operator()(uint64_t a, unsigned long long val, unsigned long long incl) const {
+    struct Staged { uint32_t slot; pos_t pos; };
+    __device__ Staged load(uint64_t a, unsigned long long val, unsigned long long) const {
+        Staged st{0, 0};
+        if (val & 1ull) { st.slot = slot[a]; st.pos = pos[a]; }
+        return st;
+    }
+    __device__ void store(uint64_t, unsigned long long val, unsigned long long incl, const Staged& st) const {
         if (val & 1ull) {
             uint32_t b = (uint32_t)incl - 1;
-            new_slot[b] = slot[a];
-            new_pos[b] = pos[a];
+            new_slot[b] = st.slot;
+            new_pos[b] = st.pos;
             new_seg[b] = (uint32_t)(incl >> 32) - 1;
         }
     }
@@ -1271,10 +1326,12 @@ __global__ void __launch_bounds__(kBlock) plcp_complete_kernel(KeySpec ks, uint6
 
 // ------------------------------------------------------------------ long runs of N (sufr_builder.rs:174-195)
 struct NRunStartIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const uint8_t* t;
     __device__ uint32_t operator()(uint64_t i) const { return (t[i] == 'N' && (i == 0 || t[i - 1] != 'N')) ? 1u : 0u; }
 };
 struct NRunEndIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const uint8_t* t;
     __device__ uint32_t operator()(uint64_t i) const { return (i > 0 && t[i] != 'N' && t[i - 1] == 'N') ? 1u : 0u; }
 };
@@ -1285,6 +1342,7 @@ struct IndexOut {
     }
 };
 struct NRunLongIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const uint64_t* starts;
     const uint64_t* ends;
     uint64_t min_len;
@@ -1333,6 +1391,7 @@ __global__ void __launch_bounds__(kBlock) n_rule_lcp_kernel(KeySpec ks, const ui
     }
 }
 struct NTieIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     KeySpec ks;
     const uint8_t* text;
     const pos_t* sa;
@@ -1370,6 +1429,7 @@ struct NTieOut {
 // ------------------------------------------------------------------ suffix filter (sufr_builder.rs:446-449)
 
 struct FilterCountIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const uint8_t* text;
     const pos_t* sa;
     __device__ uint32_t operator()(uint64_t j) const { return indexed_byte(text[sa[j]]) ? 1u : 0u; }

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(128) search_kernel(Params P, const uint8_t* __
 
 // sufr_file.rs:443-453: the entries with lcp < max_query_len, and their ranks
 struct SubsampleIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
     const void* lcp;
     int wide;
     uint64_t mql;
