@@ -776,12 +776,16 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     }
 }
 
-// isa[sa[j]] = j for the whole suffix array.  Large arrays go through one or two radix passes on the top bits of the
-// position (slices of 2^29 ranks, so the temporaries stay at 8 GB) and a windowed scatter; see isa_apply_kernel.
+// isa[sa[j]] = j for the whole suffix array.  A direct scatter of 4-byte ranks runs at ~22 G stores/s on a B200 (a
+// 32-byte sector read and written per rank; ~50 G/s even when the targets stay inside the L2:
+// profiles/r2_scatter_window.txt).  Large arrays therefore SORT the records (position, rank) on the top bits of the
+// position with the radix pass of the build, far enough that 2^chunk_bits consecutive records hold exactly the positions
+// [c << chunk_bits, (c + 1) << chunk_bits) -- the suffix array is a permutation, so the chunk boundaries need no
+// histogram -- and a block places one chunk in shared memory and writes it out as whole lines.
 void Build::isa_init(uint32_t* isa) {
-    // SUFR_B200_DEBUG_BUCKET_ISA = 1 | 2 takes the bucketed route (with that many passes) on small texts too: tests
-    const char* force = getenv("SUFR_B200_DEBUG_BUCKET_ISA");
-    const bool direct = sizeof(pos_t) != 4 || n < 4096 || (!force && n < (1ull << 26)) || getenv("SUFR_B200_DEBUG_DIRECT_ISA");
+    // SUFR_B200_DEBUG_SORT_ISA=1 takes the sorting route on small texts too (tests)
+    const bool force = getenv("SUFR_B200_DEBUG_SORT_ISA") != nullptr;
+    const bool direct = sizeof(pos_t) != 4 || n < 8192 || (!force && n < (1ull << 26)) || getenv("SUFR_B200_DEBUG_DIRECT_ISA");
     if (direct) {
         isa_init_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(n, d_sa.get(), isa);
         SUFR_KERNEL_CHECK();
@@ -790,39 +794,34 @@ void Build::isa_init(uint32_t* isa) {
     }
     if constexpr (sizeof(pos_t) == 4) {
         const int nbits = bits_for(n - 1);
-        // one pass leaves 256 buckets of the array; a second one (3 more bits) when a bucket would not sit well inside the L2
-        const bool two = force ? force[0] == '2' : ((4ull << nbits) >> 8) > (40ull << 20);
-        const uint64_t slice = force ? 10000 : 1ull << 29;
-        const uint64_t cap = std::min<uint64_t>(slice, n);
-        auto kb = dalloc<uint32_t>(cap), va = dalloc<uint32_t>(cap), vb = dalloc<uint32_t>(cap);
+        const int max_chunk = force ? 10 : kIsaChunkBitsMax;
+        const int passes = nbits > max_chunk ? (nbits - max_chunk + rsort::RADIX_BITS - 1) / rsort::RADIX_BITS : 0;
+        const int chunk_bits = std::min(max_chunk, std::max(nbits - passes * rsort::RADIX_BITS, force ? 6 : 12));
+        const int low = nbits - passes * rsort::RADIX_BITS > 0 ? nbits - passes * rsort::RADIX_BITS : 0;  // sorted bits: [low, nbits)
+        auto va = dalloc<uint32_t>(n), kb = dalloc<uint32_t>(n), vb = dalloc<uint32_t>(n);
         DevBuf<uint32_t> ka;
-        if (two) ka = dalloc<uint32_t>(cap);
+        if (passes > 1) ka = dalloc<uint32_t>(n);  // the suffix array itself is only ever read
         if (!d_counts) d_counts = dalloc<uint32_t>(rsort::counts_words());
-        for (uint64_t base = 0; base < n; base += slice) {
-            const uint64_t cnt = std::min<uint64_t>(slice, n - base);
-            uint32_t* sa_slice = reinterpret_cast<uint32_t*>(d_sa.get()) + base;  // read only: each call below is ONE pass
-            iota_kernel<<<grid_for(cnt, 4), kBlock, 0, st()>>>(va.get(), cnt, (uint32_t)base);
-            SUFR_KERNEL_CHECK();
-            const uint32_t *rk, *rv;
-            if (two) {
-                rsort::sort_pairs<uint32_t, uint32_t>(sa_slice, kb.get(), va.get(), vb.get(), cnt, nbits - 11, nbits - 8,
-                                                      d_counts.get(), st(), &ctx.launches);
-                rsort::sort_pairs<uint32_t, uint32_t>(kb.get(), ka.get(), vb.get(), va.get(), cnt, nbits - 8, nbits,
-                                                      d_counts.get(), st(), &ctx.launches);
-                rk = ka.get();
-                rv = va.get();
-            } else {
-                rsort::sort_pairs<uint32_t, uint32_t>(sa_slice, kb.get(), va.get(), vb.get(), cnt, nbits - 8, nbits,
-                                                      d_counts.get(), st(), &ctx.launches);
-                rk = kb.get();
-                rv = vb.get();
-            }
-            // every block resident at once (8 x 256 threads per SM): the grid sweeps the records ONCE, front to back
-            const uint32_t resident = (uint32_t)std::min<uint64_t>(div_up(cnt, kBlock), (uint64_t)num_sms() * 8);
-            isa_apply_kernel<<<resident, kBlock, 0, st()>>>(cnt, rk, rv, isa);
-            SUFR_KERNEL_CHECK();
-            launched(2);
+        iota_kernel<<<grid_for(n, 4), kBlock, 0, st()>>>(va.get(), n, 0u);
+        SUFR_KERNEL_CHECK();
+        const uint32_t* rk = reinterpret_cast<const uint32_t*>(d_sa.get());
+        const uint32_t* rv = va.get();
+        for (int pass = 0; pass < passes; pass++) {  // one sort_pairs call = ONE pass: in -> out
+            const int b0 = low + pass * rsort::RADIX_BITS, b1 = std::min(nbits, b0 + rsort::RADIX_BITS);
+            uint32_t* ko = (pass & 1) ? ka.get() : kb.get();
+            uint32_t* vo = (pass & 1) ? va.get() : vb.get();
+            rsort::sort_pairs<uint32_t, uint32_t>(const_cast<uint32_t*>(rk), ko, const_cast<uint32_t*>(rv), vo, n, b0, b1,
+                                                  d_counts.get(), st(), &ctx.launches);
+            rk = ko;
+            rv = vo;
         }
+        static bool attr_set[64] = {};
+        allow_dynamic_smem(isa_chunk_kernel, (size_t)4 << kIsaChunkBitsMax, attr_set);
+        const uint64_t chunks = div_up(n, 1ull << chunk_bits);
+        isa_chunk_kernel<<<(uint32_t)std::min<uint64_t>(chunks, (uint64_t)num_sms() * 8), 512, (size_t)4 << chunk_bits, st()>>>(
+            n, chunk_bits, rk, rv, isa);
+        SUFR_KERNEL_CHECK();
+        launched(2);
     }
 }
 
@@ -906,7 +905,29 @@ void Build::apply_filter() {
         auto counts = dalloc<uint32_t>(nblocks);
         auto tail_min = dalloc<uint32_t>(nblocks);
         auto offsets = dalloc<uint32_t>(nblocks);
-        filter_flags_kernel<<<nblocks, kBlock, 0, st()>>>(d_text.get(), d_sa.get(), d_lcp.get(), s, flags.get(),
+        KeepRanges ranges{};
+        if (s == n && !getenv("SUFR_B200_DEBUG_GATHER_FILTER")) {
+            // the whole text was sorted: rank ranges of the indexed first bytes from a byte histogram (KeepRanges)
+            auto d_hist = dalloc<unsigned long long>(256);
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_hist.get(), 0, 256 * 8, st()));
+            byte_hist_kernel<<<grid_for(n, 64), kBlock, 0, st()>>>(d_text.get(), n, d_hist.get());
+            SUFR_KERNEL_CHECK();
+            launched();
+            unsigned long long hist[256];
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(hist, d_hist.get(), sizeof(hist), cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            uint64_t start = 0;
+            for (int c = 0; c < 256; c++) {
+                if (hist[c] && (c == '$' || c == 'A' || c == 'C' || c == 'G' || c == 'T')) {
+                    ranges.lo[ranges.count] = start;
+                    ranges.hi[ranges.count] = start + hist[c];
+                    ranges.count++;
+                }
+                start += hist[c];
+            }
+            if (start != n) throw Error(SUFR_B200_ERR_INTERNAL, "byte histogram does not add up to the text length");
+        }
+        filter_flags_kernel<<<nblocks, kBlock, 0, st()>>>(d_text.get(), d_sa.get(), ranges, d_lcp.get(), s, flags.get(),
                                                          counts.get(), tail_min.get());
         SUFR_KERNEL_CHECK();
         launched();

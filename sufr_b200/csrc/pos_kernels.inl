@@ -1172,17 +1172,27 @@ __global__ void __launch_bounds__(kBlock) isa_init_kernel(uint64_t n, const pos_
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) isa[sa[j]] = (uint32_t)j;
 }
-// The same through records (position, rank) that a radix pass has ordered by the top bits of the position: all blocks
-// walk the records together, so the 4-byte stores of a moment fall into a window of the array that the L2 holds and
-// leave it as whole sectors (a direct scatter costs a 32-byte read and a 32-byte write of DRAM per rank).
+// Records (position, rank) sorted on the position bits above `chunk_bits`: chunk c = records [c << chunk_bits, ...) holds
+// exactly the positions [c << chunk_bits, (c + 1) << chunk_bits) in some order.  A block orders one chunk in shared
+// memory and writes the ranks as whole lines (build_impl.inl, isa_init).
+constexpr int kIsaChunkBitsMax = 14;
 __global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* __restrict__ out, uint64_t count, uint32_t base) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) out[j] = base + (uint32_t)j;
 }
-__global__ void __launch_bounds__(kBlock) isa_apply_kernel(uint64_t count, const uint32_t* __restrict__ p,
-                                                           const uint32_t* __restrict__ rank, uint32_t* __restrict__ isa) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) isa[p[j]] = rank[j];
+__global__ void __launch_bounds__(512) isa_chunk_kernel(uint64_t n, int chunk_bits, const uint32_t* __restrict__ p,
+                                                        const uint32_t* __restrict__ rank, uint32_t* __restrict__ isa) {
+    extern __shared__ uint32_t isa_local[];
+    const uint32_t size = 1u << chunk_bits, mask = size - 1u;
+    const uint64_t chunks = (n + size - 1) >> chunk_bits;
+    for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+        const uint64_t base = c << chunk_bits;
+        const uint32_t count = (n - base) < (uint64_t)size ? (uint32_t)(n - base) : size;
+        for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) isa_local[p[base + t] & mask] = rank[base + t];
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) isa[base + t] = isa_local[t];
+        __syncthreads();
+    }
 }
 
 // rank of an active element = SA slot of the first element of its group
@@ -1474,8 +1484,58 @@ struct FilterLcpOut {
 // N-starts are adjacent), so runs are few but can be millions long: a kept element looks back inside its
 // block, and past the block start it walks per-block summaries (min over a block's trailing dropped run).
 constexpr int kFilterRows = 8;
+// Ranks of the kept suffixes when the WHOLE text was sorted: the suffixes that start with one byte are adjacent in the
+// suffix array, so a byte histogram of the text gives the rank ranges of '$', 'A', 'C', 'G', 'T' and no rank has to
+// look its first byte up (a random read of the text per rank otherwise).  count == 0: look the byte up.
+struct KeepRanges {
+    uint64_t lo[5], hi[5];
+    int count;
+    __device__ bool contains(uint64_t j) const {
+        bool k = false;
+#pragma unroll
+        for (int r = 0; r < 5; r++) k |= r < count && j >= lo[r] && j < hi[r];
+        return k;
+    }
+};
+__global__ void __launch_bounds__(kBlock) byte_hist_kernel(const uint8_t* __restrict__ text, uint64_t n,
+                                                           unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nvec = (((uintptr_t)text) & 15) == 0 ? n / 16 : 0;
+    uint32_t ca = 0, cc = 0, cg = 0, ct = 0;  // the common bytes of a DNA text are counted in registers
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        if (ca > 0xFFFFFF00u || cc > 0xFFFFFF00u || cg > 0xFFFFFF00u || ct > 0xFFFFFF00u) {
+            atomicAdd(&hist['A'], (unsigned long long)ca); atomicAdd(&hist['C'], (unsigned long long)cc);
+            atomicAdd(&hist['G'], (unsigned long long)cg); atomicAdd(&hist['T'], (unsigned long long)ct);
+            ca = cc = cg = ct = 0;
+        }
+        const uint4 x = reinterpret_cast<const uint4*>(text)[v];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t ea = swar_eq(w[k], 0x41414141u), ec = swar_eq(w[k], 0x43434343u);
+            const uint32_t eg = swar_eq(w[k], 0x47474747u), et = swar_eq(w[k], 0x54545454u);
+            ca += __popc(ea); cc += __popc(ec); cg += __popc(eg); ct += __popc(et);
+            const uint32_t acgt = ea | ec | eg | et;
+            if (acgt != 0x80808080u) {
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (!((acgt >> (8 * b + 7)) & 1u)) atomicAdd(&h[(w[k] >> (8 * b)) & 0xFFu], 1u);
+            }
+        }
+    }
+    for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&h[text[i]], 1u);
+    if (ca) atomicAdd(&hist['A'], (unsigned long long)ca);
+    if (cc) atomicAdd(&hist['C'], (unsigned long long)cc);
+    if (cg) atomicAdd(&hist['G'], (unsigned long long)cg);
+    if (ct) atomicAdd(&hist['T'], (unsigned long long)ct);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
 __global__ void __launch_bounds__(kBlock) filter_flags_kernel(const uint8_t* __restrict__ text,
-                                                              const pos_t* __restrict__ sa,
+                                                              const pos_t* __restrict__ sa, KeepRanges ranges,
                                                               const uint32_t* __restrict__ lcp, uint64_t s,
                                                               uint32_t* __restrict__ flags32,
                                                               uint32_t* __restrict__ block_counts,
@@ -1490,7 +1550,7 @@ __global__ void __launch_bounds__(kBlock) filter_flags_kernel(const uint8_t* __r
 #pragma unroll
     for (int r = 0; r < kFilterRows; r++) {
         uint64_t j = base + (uint64_t)r * kBlock + threadIdx.x;
-        bool keep = j < s && indexed_byte(text[sa[j]]);
+        bool keep = j < s && (ranges.count ? ranges.contains(j) : indexed_byte(text[sa[j]]));
         unsigned m = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) {
             flags32[(base + (uint64_t)r * kBlock) / 32 + warp] = m;

@@ -179,18 +179,20 @@ def test_tandem_repeats_use_prefix_doubling(S, unit, copies):
     gpu_vs_oracle(S, text, is_dna=True, index_bits=64)
 
 
-@pytest.mark.parametrize("passes", ["1", "2"])
-def test_bucketed_inverse_suffix_array(S, monkeypatch, passes):
-    """Texts above 2^26 bytes fill the inverse suffix array through radix passes on the position (windowed scatter);
-    forced here on a small text, in several slices, with one and with two passes."""
-    monkeypatch.setenv("SUFR_B200_DEBUG_BUCKET_ISA", passes)
-    rng = random.Random(int(passes))
+def test_sorted_inverse_suffix_array(S, monkeypatch):
+    """Texts above 2^26 bytes fill the inverse suffix array by sorting (position, rank) on the top position bits and
+    placing chunks in shared memory; forced here on small texts (one and two radix passes, a partial last chunk)."""
+    monkeypatch.setenv("SUFR_B200_DEBUG_SORT_ISA", "1")
+    rng = random.Random(11)
     text = rand_text(rng, 30_000, b"ACGT")[:-1] + b"ACGGT" * 6000 + rand_text(rng, 9000, b"ACGT", repeat_p=0.3, max_rep=400)[:-1] \
         + b"ACGGT" * 2500 + b"$"
     _, _, doubling = gpu_vs_oracle(S, text, is_dna=True)
     assert doubling > 0
     gpu_vs_oracle(S, text, is_dna=True, index_bits=64)
     gpu_vs_oracle(S, text)
+    big = rand_text(rng, 200_000, b"ACGT")[:-1] + b"AACCGGTTAC" * 9000 + b"$"   # 18 position bits: two passes
+    _, _, doubling = gpu_vs_oracle(S, big, is_dna=True)
+    assert doubling > 0
 
 
 def n_run_text(rng, runs, filler=400):
