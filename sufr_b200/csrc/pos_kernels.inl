@@ -1504,12 +1504,13 @@ __global__ void __launch_bounds__(kBlock) byte_hist_kernel(const uint8_t* __rest
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t nvec = (((uintptr_t)text) & 15) == 0 ? n / 16 : 0;
-    uint32_t ca = 0, cc = 0, cg = 0, ct = 0;  // the common bytes of a DNA text are counted in registers
+    uint32_t ca = 0, cc = 0, cg = 0, ct = 0, cn = 0;  // the common bytes of a DNA text are counted in registers
     for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        if (ca > 0xFFFFFF00u || cc > 0xFFFFFF00u || cg > 0xFFFFFF00u || ct > 0xFFFFFF00u) {
+        if ((ca | cc | cg | ct | cn) > 0x7FFFFF00u) {
             atomicAdd(&hist['A'], (unsigned long long)ca); atomicAdd(&hist['C'], (unsigned long long)cc);
             atomicAdd(&hist['G'], (unsigned long long)cg); atomicAdd(&hist['T'], (unsigned long long)ct);
-            ca = cc = cg = ct = 0;
+            atomicAdd(&hist['N'], (unsigned long long)cn);
+            ca = cc = cg = ct = cn = 0;
         }
         const uint4 x = reinterpret_cast<const uint4*>(text)[v];
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
@@ -1518,7 +1519,12 @@ __global__ void __launch_bounds__(kBlock) byte_hist_kernel(const uint8_t* __rest
             const uint32_t ea = swar_eq(w[k], 0x41414141u), ec = swar_eq(w[k], 0x43434343u);
             const uint32_t eg = swar_eq(w[k], 0x47474747u), et = swar_eq(w[k], 0x54545454u);
             ca += __popc(ea); cc += __popc(ec); cg += __popc(eg); ct += __popc(et);
-            const uint32_t acgt = ea | ec | eg | et;
+            uint32_t acgt = ea | ec | eg | et;
+            if (acgt != 0x80808080u) {  // runs of N (masked regions) would serialise on one shared counter
+                const uint32_t en = swar_eq(w[k], 0x4E4E4E4Eu);
+                cn += __popc(en);
+                acgt |= en;
+            }
             if (acgt != 0x80808080u) {
 #pragma unroll
                 for (int b = 0; b < 4; b++)
@@ -1531,6 +1537,7 @@ __global__ void __launch_bounds__(kBlock) byte_hist_kernel(const uint8_t* __rest
     if (cc) atomicAdd(&hist['C'], (unsigned long long)cc);
     if (cg) atomicAdd(&hist['G'], (unsigned long long)cg);
     if (ct) atomicAdd(&hist['T'], (unsigned long long)ct);
+    if (cn) atomicAdd(&hist['N'], (unsigned long long)cn);
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
