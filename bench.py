@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--cpu-baseline-sample", type=int, default=400_000_000,
                     help="bases of the one cpu_baseline build inside our own arm (about 15-20 s of CPU work)")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (1, 3, 4, 5, 2b)")
+    ap.add_argument("--no-e2e-file", action="store_true", help="skip the host text -> .sufr file figure")
     ap.add_argument("--configs", default="config1,config3,config4,config5,config2b")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -302,6 +303,11 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, S, ctx, d_text, text_len, bargs, rank, world, dev, barrier)
 
+    # ---------------- e2e_file: host text in, one `.sufr` file out (sufr::create through the C ABI), N=1 only
+    e2e_file = None
+    if not args.no_e2e and not args.no_e2e_file and world == 1:
+        e2e_file = run_e2e_file(args, S, ctx, d_text, text_len, bargs, total_suffixes, dev)
+
     # ---------------- CPU baseline on a bounded prefix (rank 0, N=1 only)
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:
@@ -342,7 +348,7 @@ def main():
             "dtype": "u64" if args.index_bits == 64 else "u32", "data": "synthetic",
             "config": workload_config(args, text_len),
             "clocks": clocks.summary(),
-            "e2e": e2e, "gpu_launches": launches,
+            "e2e": e2e, "e2e_file": e2e_file, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "osort::onesweep_kernel<u64,u32,512,16> = radix scatter pass of the main sort",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
@@ -518,6 +524,47 @@ def run_e2e(args, S, ctx, d_text, text_len, bargs, rank, world, dev, barrier):
             "ms_per_step": 1e3 * elapsed / args.e2e_steps, "steps": args.e2e_steps,
             "note": "pinned host text -> H2D -> build -> D2H (LCP as bytes + exceptions, u64 SA as u32, widened by host "
                     "threads into the pinned u64 result arrays), per step; bytes are those of rank 0"}
+
+
+def run_e2e_file(args, S, ctx, d_text, text_len, bargs, total_suffixes, dev):
+    """Host text -> one `.sufr` file on a RAM disk, through sufr_b200_create_multi (what `sufr-b200 create` calls):
+    upload, build, and the file written straight from device memory by the streaming writer.  One run (the file
+    is new every time, as for a user); skipped when the box cannot hold the file in RAM."""
+    import copy
+    import shutil
+    import torch
+    w = args.index_bits // 8
+    file_bytes = text_len + 2 * total_suffixes * w + 4096
+    h = d_text.cpu().numpy()
+    torch.cuda.synchronize()
+    ctx.trim()  # the call below works in a context of its own: give the pooled device and pinned memory back first
+    torch.cuda.empty_cache()
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    shm_free = shutil.disk_usage("/dev/shm").free if os.path.isdir("/dev/shm") else 0
+    if avail < file_bytes * 1.2 + text_len + (8 << 30) or shm_free < file_bytes * 1.05:
+        return {"skipped": f"needs {file_bytes / 1e9:.1f} GB of RAM disk; available RAM {avail / 1e9:.1f} GB, "
+                           f"/dev/shm free {shm_free / 1e9:.1f} GB"}
+    path = f"/dev/shm/sufr_b200_bench_{os.getpid()}.sufr"
+    b = copy.copy(bargs)
+    b.text = memoryview(h)
+    b.path = path
+    try:
+        t0 = time.perf_counter()
+        res = S.create_multi(b, [dev.index or 0], args.index_bits)
+        dt = time.perf_counter() - t0
+        size = os.path.getsize(path)
+        return {"value": res["num_suffixes"] / dt, "unit": "suffixes/s", "s": dt, "file_bytes": size, "path": "/dev/shm",
+                "device_ms": res["timings"]["total_ms"], "write_ms": res["timings"].get("d2h_ms"),
+                "note": "host text -> sufr_b200_create_multi on this GPU -> .sufr (version 6) on a RAM disk, one run, wall clock"}
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
 
 
 def _with_text(bargs, h_text):
