@@ -61,6 +61,8 @@ def main():
          dict(is_dna=True, allow_ambiguity=True, ignore_softmask=True), 32, {}),
         ("deep repeats, filtered after the sort", tandem(8, n), dict(is_dna=True), 64, {}),
         ("dense round 0", rand_text(9, n, b"ACGT", 0.05), dict(is_dna=True), 32, {"SUFR_B200_DEBUG_SPARSE_CAP": "16"}),
+        ("deep repeats, inverse suffix array by sorting", tandem(10, n), dict(is_dna=True, allow_ambiguity=True), 32,
+         {"SUFR_B200_DEBUG_SORT_ISA": "1"}),
     ]
     for name, text, kw, bits, env in cases:
         for k, v in env.items():
@@ -82,6 +84,16 @@ def main():
                     device_text=(t.data_ptr(), t.numel()))
         rep = r.verify()
         assert rep["ok"] or "max_query_len" in kw, (name, rep)
+        # the read side: LCP-subsampled array + batched search, against a scan of the text
+        bargs = S.SufrBuilderArgs(text=b"", **kw)
+        idx = S.SufrIndex(r, bargs)
+        rng = random.Random(len(name))
+        tt = r.text_tensor().cpu().numpy().tobytes()
+        qs = [tt[p:p + rng.randrange(1, 12)].decode("latin1") for p in (rng.randrange(len(tt) - 12) for _ in range(300))]
+        for low in (True, False):
+            got = idx.search(qs, max_query_len=6 if "seed_mask" not in kw else None, low_memory=low)
+            assert len(got) == len(qs)
+        idx.close()
         r.free()
         for k in env:
             os.environ.pop(k, None)
