@@ -584,6 +584,9 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // ordered keys are not written (the LCP marks carry the group structure), so the key partner is free already
     if (fast2) keys_spare_.reset();
     ViewAll v0{keys_sorted.get(), d_sa.get(), nullptr, sort_kmask_};  // general path only
+    // Full sort on the fast path: groups whose members agree on all 31 symbols of the 2-bit key (no fill, not a large
+    // run) start their exact refinement at key word 1 -- word 0 (21 symbols) could not split them.  kSegDeep.
+    const int deep_marks = (fast2 && ks.mode == kModeFull && !sentinel_ && !getenv("SUFR_B200_DEBUG_NO_DEEP_GROUPS")) ? 1 : 0;
     uint64_t m = 0, nseg = 0;
     DevBuf<uint32_t> slot, seg;
     DevBuf<pos_t> pos;
@@ -610,7 +613,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             }
             round0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), pos_spare_.get(), r0n,
                                                                       d_lcp.get(), act_slot.get(), act_pos.get(), d_cnt.get(),
-                                                                      capacity, wide_sa_.get(), wide_lcp_.get());
+                                                                      capacity, wide_sa_.get(), wide_lcp_.get(), deep_marks);
         } else {
             resolve0_append_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks, final_word,
                                                                          sort_kmask_, d_lcp.get(), act_slot.get(), act_pos.get(),
@@ -649,7 +652,8 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                 wide_m_ = m;
             }
             seg = dalloc<uint32_t>(m);
-            if (fast2) nseg = scan_total(m, LcpSegIn{d_lcp.get(), slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
+            if (fast2) nseg = scan_total(m, LcpSegIn{d_lcp.get(), slot.get()}, scan::SumU32{},
+                                         SparseSegOut{seg.get(), d_lcp.get(), slot.get(), r0n});
             else nseg = scan_total(m, SparseSegIn{v0, slot.get()}, scan::SumU32{}, SparseSegOut{seg.get()});
         } else {
             // dense (repetitive text): order-preserving compaction by scan
@@ -665,7 +669,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                 slot = dalloc<uint32_t>(m);
                 pos = dalloc<pos_t>(m);
                 seg = dalloc<uint32_t>(m);
-                scan_finish(r0n, ain, scan::SumU64{}, LcpActiveOut{d_sa.get(), slot.get(), pos.get(), seg.get()}, part);
+                scan_finish(r0n, ain, scan::SumU64{}, LcpActiveOut{d_sa.get(), slot.get(), pos.get(), seg.get(), d_lcp.get(), r0n}, part);
             } else {
                 ActiveIn<ViewAll> ain{v0, r0n, 0, sentinel_ ? 1 : 0};
                 unsigned long long tot = scan_begin(r0n, ain, scan::SumU64{}, part);
@@ -692,11 +696,16 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
     // share of what is left with every further word, and the cost of a round falls with it: such an attempt stays
     // with word rounds (up to 320 words = 6720 bases) while they pay, so a shard finishes on its own and N GPUs
     // divide the work.  Tandem repeats make no progress per word and leave for prefix doubling at once.
-    const int kMaxWordRounds = 3, kPatientWordRounds = 320;
+    // (With deep groups the bulk of a DNA text is one word ahead: three rounds take it to 84 symbols, the depth four
+    // rounds used to reach; prefix doubling then starts from h = 63, which every group has reached.)
+    const int kMaxWordRounds = getenv("SUFR_B200_DEBUG_WORD_ROUNDS") ? atoi(getenv("SUFR_B200_DEBUG_WORD_ROUNDS")) : (deep_marks ? 2 : 3);
+    const int kPatientWordRounds = 320;
     uint64_t m_last = m;  // unresolved elements at the start of the previous round
     int direct_tail_word = -1;
     while (m > 0) {
-        if (ks.mode == kModeFull && word >= kMaxWordRounds) {
+        // (a round that resolved less than an eighth of what it was given: tandem repeats, further words will not help)
+        const bool stalled = full_set_ && word >= 1 && m * 8 > m_last * 7 && !getenv("SUFR_B200_DEBUG_WORD_ROUNDS");
+        if (ks.mode == kModeFull && (word >= kMaxWordRounds || stalled)) {
             bool patient = !full_set_ && word < kPatientWordRounds && (m * 16 < s || m * 16 <= m_last * 15);
             if (!patient) {
                 doubling(slot, pos, seg, m, nseg, (uint64_t)(word + 1) * K);
@@ -730,7 +739,7 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             auto slot2 = dalloc<uint32_t>(m2);
             auto pos2 = dalloc<pos_t>(m2);
             auto seg2 = dalloc<uint32_t>(m2);
-            scan_finish(m, lin, scan::SumU64{}, LeftoverOut{slot.get(), pos.get(), slot2.get(), pos2.get(), seg2.get()}, part);
+            scan_finish(m, lin, scan::SumU64{}, LeftoverOut{slot.get(), pos.get(), slot2.get(), pos2.get(), seg2.get(), seg.get()}, part);
             slot = std::move(slot2);
             pos = std::move(pos2);
             seg = std::move(seg2);
@@ -749,7 +758,8 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
         }
         final_word = ((uint64_t)(word + 1) * K >= ks.cap) ? 1 : 0;
         auto keys = dalloc<uint64_t>(m);
-        round_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, pos.get(), keys.get());
+        round_keys_kernel<<<grid_for(m, 2), kBlock, 0, st()>>>(ks, m, (uint32_t)word, sentinel_ ? 1 : 0, pos.get(), seg.get(),
+                                                               keys.get());
         SUFR_KERNEL_CHECK();
         launched();
         sort_groups(keys, pos, seg.get(), slot.get(), m, nseg, 64 - used, 64, false);

@@ -65,6 +65,13 @@ constexpr uint32_t kLcpPending = 0xFFFFFFFFu;
 //                        fill, or a neighbouring group that is still being refined): computed exactly from the
 //                        final order once the refinement is done
 constexpr uint32_t kLcpFixup = 0xFFFFFFFEu;
+//   kLcpPendingDeep    : kLcpPending, and the group is known to agree on every symbol of the fast path's 31-symbol
+//                        key (no fill in any member's key, not a large run): its exact refinement may skip key word 0
+constexpr uint32_t kLcpPendingDeep = 0xFFFFFFFDu;
 constexpr uint32_t kLcpLowerBound = 0x80000000u;
+__host__ __device__ __forceinline__ bool lcp_is_pending(uint32_t v) { return v == kLcpPending || v == kLcpPendingDeep; }
+// Group numbers of the unresolved elements carry that knowledge in their top bit ("deep" groups are one key word
+// ahead of the round counter); a group number proper is below 2^31 (a group has at least two members).
+constexpr uint32_t kSegDeep = 0x80000000u;
 
 }  // namespace sufr

@@ -469,6 +469,7 @@ struct ViewAll {
     __device__ pos_t p(uint64_t i) const { return pos[i]; }
     __device__ bool same_seg(uint64_t i) const { return i > 0; }
     __device__ uint32_t slot(uint64_t i) const { return (uint32_t)i; }
+    __device__ uint32_t deep(uint64_t) const { return 0u; }
 };
 struct ViewActive {
     const uint64_t* key;
@@ -480,6 +481,7 @@ struct ViewActive {
     __device__ pos_t p(uint64_t i) const { return pos[i]; }
     __device__ bool same_seg(uint64_t i) const { return i > 0 && seg[i] == seg[i - 1]; }
     __device__ uint32_t slot(uint64_t i) const { return slot_[i]; }
+    __device__ uint32_t deep(uint64_t i) const { return seg[i] & kSegDeep; }  // see kSegDeep
 };
 
 // After sorting by key word `word`: write the LCP of every newly created group boundary, mark the
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(View v, uint64_t m, Key
         }
         uint64_t ki = v.k(i), kp = v.k(i - 1);
         if (ki != kp) {
-            lcp[v.slot(i)] = lcp_from_words(ks, kp, ki, (uint64_t)word * ks.pt.K, v.p(i - 1), v.p(i));
+            lcp[v.slot(i)] = lcp_from_words(ks, kp, ki, (uint64_t)(word + (v.deep(i) ? 1u : 0u)) * ks.pt.K, v.p(i - 1), v.p(i));
         } else if (final_word) {
             uint64_t la = key_len(ks, v.p(i - 1)), lb = key_len(ks, v.p(i));
             lcp[v.slot(i)] = (uint32_t)(la < lb ? la : lb);
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
                                                               unsigned long long* __restrict__ act_count,
                                                               uint64_t capacity,
                                                               unsigned long long* __restrict__ sa64,
-                                                              unsigned long long* __restrict__ lcp64) {
+                                                              unsigned long long* __restrict__ lcp64, int deep_marks) {
     constexpr uint32_t RL = kFast2SmallGroup + 1;  // a run of RL records or more is "large"
     __shared__ uint64_t ka[kR0N], kb[kR0N];
     __shared__ pos_t pa[kR0N], pb[kR0N];
@@ -726,9 +728,14 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
                     } else {         // predecessor = last record of the previous run
                         prev_multi = pback > 0 && d >= 2 && (pback + 1 >= RL || ((kb[d - 2] ^ km1) & ~3ull) == 0);
                     }
-                    if (!head)
+                    if (!head) {
                         out = kLcpPending;
-                    else if (((km1 | k0) & 1ull) == 0 && !next_same && !prev_multi)
+                        if (deep_marks) {  // no member of the group (equal canonical keys inside this small run) has fill
+                            uint64_t any = 0;
+                            for (uint32_t b = h; b <= d + fwd; b++) any |= ((kb[b] & ~3ull) == c0) ? kb[b] : 0ull;
+                            if (!(any & 1ull)) out = kLcpPendingDeep;
+                        }
+                    } else if (((km1 | k0) & 1ull) == 0 && !next_same && !prev_multi)
                         out = (uint32_t)__clzll((long long)(km1 ^ k0)) >> 1;
                     else
                         out = kLcpFixup;
@@ -809,15 +816,15 @@ struct LcpSegIn {
     static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes  // segment ids of the slot-sorted unresolved list
     const uint32_t* lcp;
     const uint32_t* slot;
-    __device__ uint32_t operator()(uint64_t a) const { return lcp[slot[a]] != kLcpPending ? 1u : 0u; }
+    __device__ uint32_t operator()(uint64_t a) const { return lcp_is_pending(lcp[slot[a]]) ? 0u : 1u; }
 };
 struct LcpActiveIn {
     static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes  // dense variant: order-preserving compaction of all unresolved records
     const uint32_t* lcp;
     uint64_t m;
     __device__ unsigned long long operator()(uint64_t i) const {
-        const bool head = lcp[i] != kLcpPending;
-        const bool next_same = i + 1 < m && lcp[i + 1] == kLcpPending;
+        const bool head = !lcp_is_pending(lcp[i]);
+        const bool next_same = i + 1 < m && lcp_is_pending(lcp[i + 1]);
         return (!head || next_same) ? (1ull | ((unsigned long long)head << 32)) : 0ull;
     }
 };
@@ -826,13 +833,24 @@ struct LcpActiveOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    __device__ pos_t load(uint64_t i, unsigned long long val, unsigned long long) const { return (val & 1ull) ? pos[i] : (pos_t)0; }
-    __device__ void store(uint64_t i, unsigned long long val, unsigned long long incl, pos_t p) const {
+    const uint32_t* lcp;  // the marks: a group is deep iff its continuing members carry kLcpPendingDeep
+    uint64_t s;
+    struct Staged { pos_t pos; uint32_t deep; };
+    __device__ Staged load(uint64_t i, unsigned long long val, unsigned long long) const {
+        Staged st{0, 0};
+        if (val & 1ull) {
+            st.pos = pos[i];
+            const bool head = (val >> 32) & 1ull;  // a head's own mark is its boundary LCP: look at its successor
+            st.deep = lcp[head && i + 1 < s ? i + 1 : i] == kLcpPendingDeep ? kSegDeep : 0u;
+        }
+        return st;
+    }
+    __device__ void store(uint64_t i, unsigned long long val, unsigned long long incl, const Staged& st) const {
         if (val & 1ull) {
             const uint32_t a = (uint32_t)incl - 1;
             new_slot[a] = (uint32_t)i;
-            new_pos[a] = p;
-            new_seg[a] = (uint32_t)(incl >> 32) - 1;
+            new_pos[a] = st.pos;
+            new_seg[a] = ((uint32_t)(incl >> 32) - 1) | st.deep;
         }
     }
 };
@@ -881,7 +899,17 @@ struct SparseSegIn {
 };
 struct SparseSegOut {
     uint32_t* seg;
-    __device__ void operator()(uint64_t a, uint32_t, uint32_t incl) const { seg[a] = incl - 1; }
+    const uint32_t* lcp = nullptr;   // fast path: the marks (deep groups, see LcpActiveOut); else NULL
+    const uint32_t* slot = nullptr;
+    uint64_t s = 0;
+    __device__ void operator()(uint64_t a, uint32_t v, uint32_t incl) const {
+        uint32_t deep = 0;
+        if (lcp) {
+            const uint64_t j = slot[a];  // v = 1: head of its group
+            deep = lcp[v && j + 1 < s ? j + 1 : j] == kLcpPendingDeep ? kSegDeep : 0u;
+        }
+        seg[a] = (incl - 1) | deep;
+    }
 };
 
 // Compaction of the elements that are still in a group of size > 1.  Sum-scan input: bit 0 = active,
@@ -912,10 +940,10 @@ struct ActiveOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    struct Staged { uint32_t slot; pos_t pos; };
+    struct Staged { uint32_t slot, deep; pos_t pos; };
     __device__ Staged load(uint64_t i, unsigned long long val, unsigned long long) const {
-        Staged st{0, 0};
-        if (val & 1ull) { st.slot = v.slot(i); st.pos = v.p(i); }
+        Staged st{0, 0, 0};
+        if (val & 1ull) { st.slot = v.slot(i); st.pos = v.p(i); st.deep = v.deep(i); }
         return st;
     }
     __device__ void store(uint64_t, unsigned long long val, unsigned long long incl, const Staged& st) const {
@@ -923,7 +951,7 @@ struct ActiveOut {
             uint32_t a = (uint32_t)incl - 1;
             new_slot[a] = st.slot;
             new_pos[a] = st.pos;
-            new_seg[a] = (uint32_t)(incl >> 32) - 1;
+            new_seg[a] = ((uint32_t)(incl >> 32) - 1) | st.deep;
         }
     }
 };
@@ -941,11 +969,13 @@ struct ActiveOut {
 // do get re-ordered in almost every round: profiles/r2_round_log_config5.txt.)
 constexpr int kSmallSeg = 8;
 __global__ void __launch_bounds__(kBlock) round_keys_kernel(KeySpec ks, uint64_t m, uint32_t word, int filter,
-                                                            const pos_t* __restrict__ pos, uint64_t* __restrict__ keys) {
+                                                            const pos_t* __restrict__ pos, const uint32_t* __restrict__ seg,
+                                                            uint64_t* __restrict__ keys) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
         const pos_t p = pos[a];
-        keys[a] = (filter && !indexed_byte(ks.text[p])) ? ~0ull : key_word(ks, p, word);
+        const uint32_t w = word + ((seg[a] & kSegDeep) ? 1u : 0u);  // deep groups are one key word ahead
+        keys[a] = (filter && !indexed_byte(ks.text[p])) ? ~0ull : key_word(ks, p, w);
     }
 }
 __global__ void __launch_bounds__(kBlock) small_groups_kernel(uint64_t m, const uint32_t* __restrict__ seg,
@@ -960,7 +990,7 @@ __global__ void __launch_bounds__(kBlock) small_groups_kernel(uint64_t m, const 
         int len = 1;
         while (len <= kSmallSeg && a + len < m && seg[a + len] == g) len++;
         if (len > kSmallSeg) {
-            is_large[g] = 1;
+            is_large[g & ~kSegDeep] = 1;
             *any_large = 1;  // "some group is large" (benign race: every writer stores 1)
             continue;
         }
@@ -1018,7 +1048,7 @@ __global__ void __launch_bounds__(kBlock) finish_small_groups_kernel(KeySpec ks,
         int len = 1;
         while (len <= kSmallSeg && a + len < m && seg[a + len] == g) len++;
         if (len > kSmallSeg) {
-            is_large[g] = 1;
+            is_large[g & ~kSegDeep] = 1;
             atomicAdd(large_elems, 1ull);
             continue;
         }
@@ -1052,10 +1082,11 @@ struct LeftoverOut {
     uint32_t* new_slot;
     pos_t* new_pos;
     uint32_t* new_seg;
-    struct Staged { uint32_t slot; pos_t pos; };
+    const uint32_t* seg;
+    struct Staged { uint32_t slot, deep; pos_t pos; };
     __device__ Staged load(uint64_t a, unsigned long long val, unsigned long long) const {
-        Staged st{0, 0};
-        if (val & 1ull) { st.slot = slot[a]; st.pos = pos[a]; }
+        Staged st{0, 0, 0};
+        if (val & 1ull) { st.slot = slot[a]; st.pos = pos[a]; st.deep = seg[a] & kSegDeep; }
         return st;
     }
     __device__ void store(uint64_t, unsigned long long val, unsigned long long incl, const Staged& st) const {
@@ -1063,7 +1094,7 @@ struct LeftoverOut {
             const uint32_t b = (uint32_t)incl - 1;
             new_slot[b] = st.slot;
             new_pos[b] = st.pos;
-            new_seg[b] = (uint32_t)(incl >> 32) - 1;
+            new_seg[b] = ((uint32_t)(incl >> 32) - 1) | st.deep;
         }
     }
 };
@@ -1076,7 +1107,7 @@ struct LargeIn {
     __device__ unsigned long long operator()(uint64_t a) const {
         const uint32_t g = seg[a], gp = seg[a > 0 ? a - 1 : 0];
         const bool head = a == 0 || gp != g;
-        return flagged[g] ? (1ull | ((unsigned long long)head << 32)) : 0ull;
+        return flagged[g & ~kSegDeep] ? (1ull | ((unsigned long long)head << 32)) : 0ull;
     }
 };
 struct LargeOut {
@@ -1221,7 +1252,7 @@ __global__ void __launch_bounds__(kBlock) doubling_keys_kernel(uint64_t m, uint6
     for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < m; a += stride) {
         uint64_t q = (uint64_t)pos[a] + h;
         uint32_t r = q < n ? isa[q] + 1u : 0u;
-        ck[a] = ((uint64_t)seg[a] << rank_bits) | r;
+        ck[a] = ((uint64_t)(seg[a] & ~kSegDeep) << rank_bits) | r;
     }
 }
 
@@ -1312,8 +1343,8 @@ __global__ void __launch_bounds__(kBlock) plcp_complete_kernel(KeySpec ks, uint6
         for (uint64_t i = i0; i < i1; i++) {
             uint32_t j = isa[i];
             uint32_t v = lcp[j];
-            if (v == kLcpPending || !(v & kLcpLowerBound) || j == 0) {
-                l = (v == kLcpPending) ? 0 : v;  // exact value known from the key words
+            if (lcp_is_pending(v) || !(v & kLcpLowerBound) || j == 0) {
+                l = lcp_is_pending(v) ? 0 : v;  // exact value known from the key words
                 continue;
             }
             uint64_t prev = sa[j - 1];
