@@ -8,7 +8,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-os.environ["SUFR_B200_LOG_ROUNDS"] = "1"
+if not os.environ.get("SUFR_NO_ROUND_LOG"):
+    os.environ["SUFR_B200_LOG_ROUNDS"] = "1"
 import torch  # noqa: E402
 import sufr_b200 as S  # noqa: E402
 import workloads  # noqa: E402
@@ -19,7 +20,7 @@ full = {"config2b": 3_100_000_000, "config5": 1_000_000_000, "config3": 1_000_00
 w = workloads.ALL[name](int(full[name] * scale))
 t = torch.frombuffer(bytearray(w.text), dtype=torch.uint8).cuda()
 args = S.SufrBuilderArgs(text=b"", sequence_starts=w.sequence_starts, sequence_names=w.sequence_names, **w.flags)
-for i in range(2):
+for i in range(int(os.environ.get("SUFR_BUILDS", "2"))):
     print(f"--- build {i}", file=sys.stderr, flush=True)
     if i == 1 and os.environ.get("SUFR_PROFILE"):  # ncu --profile-from-start off: the second build only
         torch.cuda.synchronize()
