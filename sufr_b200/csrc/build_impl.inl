@@ -375,7 +375,53 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
     // key ~0 and drop off the end of the sorted array.  Needs an unused low bit in the packed word.
     const bool sentinel = prefilter && !sharded && used_bits < 64 && kept < n && (n - kept) * 16 <= n;
     sentinel_ = sentinel;
-    if (sharded && ks.mode == kModeFull) {
+    // Measured and NOT the default: selection FUSED with key generation and the first radix pass, as on one GPU -- the
+    // shard's records are written once, already in first-digit order, and the sort proper has three passes left.  The
+    // fused kernels pay their per-POSITION cost (two key computations, tile staging) over the whole text, the selection
+    // kernel only a 32-bit test: one shard of the 3.1 Gbp text takes 84.5 -> 83.7 ms of 2, 46.3 -> 54.1 ms of 4,
+    // 27.1 -> 39.1 ms of 8.  Kept behind SUFR_B200_DEBUG_SHARD_FUSE=1 (tested: test_shard_selection_fused_...).
+    const char* fuse_env = getenv("SUFR_B200_DEBUG_SHARD_FUSE");
+    const bool fuse_shard = sharded && ks.mode == kModeFull && ks.fast2 && !descending && n > 0 && sizeof(pos_t) == 4 &&
+                            (fuse_env && atoi(fuse_env) != 0);
+    if (fuse_shard) {
+        static bool attr_set[64] = {};
+        allow_dynamic_smem(fast2_keygen_scatter_kernel, kKsSmem, attr_set);
+        const uint64_t tiles = div_up(n, kKsTile);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms() * 4);
+        const uint64_t chunk = div_up(tiles, grid) * kKsTile;
+        const uint32_t used_grid = (uint32_t)div_up(n, chunk);
+        const int shift = 64 - kFast2SortBits;
+        const uint32_t bins = 1u << kShardHistBits;
+        const uint32_t bin0 = (uint32_t)(lo >> (64 - kShardHistBits));
+        const uint32_t bin1 = hi == 0 ? bins : (uint32_t)(hi >> (64 - kShardHistBits));
+        // an empty shard ([max, max)) keeps span = 0 out of the kernels' "everything" meaning: nothing to do at all
+        KeyRange range{bin0, bin1 > bin0 ? bin1 - bin0 : 0u};
+        unsigned long long c = 0;
+        if (range.span) {
+            d_counts = dalloc<uint32_t>(rsort::counts_words());
+            auto d_cnt = dalloc<unsigned long long>(1);
+            SUFR_CUDA_CHECK(cudaMemsetAsync(d_cnt.get(), 0, 8, st()));
+            fast2_first_digit_hist_kernel<<<used_grid, kBlock, 0, st()>>>(ks, n, prefilter ? 1 : 0, chunk, shift, d_counts.get(),
+                                                                         range, d_cnt.get());
+            SUFR_KERNEL_CHECK();
+            rsort::scan_counts_kernel<<<1, 1024, 0, st()>>>(d_counts.get(), (uint32_t)rsort::RADIX * used_grid);
+            SUFR_KERNEL_CHECK();
+            SUFR_CUDA_CHECK(cudaMemcpyAsync(&c, d_cnt.get(), 8, cudaMemcpyDeviceToHost, st()));
+            SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+            if (c > 0xFFFFFFFFull) throw Error(SUFR_B200_ERR_UNSUPPORTED, "a shard holds 2^32 suffixes or more: use more GPUs");
+        }
+        s = c;
+        sort_n = s;
+        keys_a = dalloc<uint64_t>(s);
+        pos_a = dalloc<pos_t>(s);
+        if (s) {
+            fast2_keygen_scatter_kernel<<<used_grid, kBlock, kKsSmem, st()>>>(ks, n, prefilter ? 1 : 0, keys_a.get(), pos_a.get(),
+                                                                            chunk, shift, d_counts.get(), range);
+            SUFR_KERNEL_CHECK();
+            launched(3);
+            first_digit_done = true;
+        }
+    } else if (sharded && ks.mode == kModeFull) {
         // unordered selection: one key computation per position, capacity from the sampled histogram
         uint64_t capacity = shard_estimate + shard_estimate / 16 + (1u << 20);
         auto d_cnt = dalloc<unsigned long long>(1);
@@ -432,12 +478,13 @@ void Build::make_keys_and_sort(DevBuf<uint64_t>& keys_sorted, bool prefilter, bo
                 const int shift = 64 - kFast2SortBits;
                 d_counts = dalloc<uint32_t>(rsort::counts_words());
                 fast2_first_digit_hist_kernel<<<used_grid, kBlock, 0, st()>>>(ks, n, sentinel ? 1 : 0, chunk, shift,
-                                                                             d_counts.get());
+                                                                             d_counts.get(), KeyRange{0, 0}, nullptr);
                 SUFR_KERNEL_CHECK();
                 rsort::scan_counts_kernel<<<1, 1024, 0, st()>>>(d_counts.get(), (uint32_t)rsort::RADIX * used_grid);
                 SUFR_KERNEL_CHECK();
                 fast2_keygen_scatter_kernel<<<used_grid, kBlock, kKsSmem, st()>>>(ks, n, sentinel ? 1 : 0, keys_a.get(),
-                                                                                pos_a.get(), chunk, shift, d_counts.get());
+                                                                                pos_a.get(), chunk, shift, d_counts.get(),
+                                                                                KeyRange{0, 0});
                 launched(2);
                 first_digit_done = true;
             } else

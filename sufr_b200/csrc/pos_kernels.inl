@@ -75,10 +75,19 @@ __device__ __forceinline__ uint64_t fast2_lane_key(const KeySpec& ks, const Fast
 }
 constexpr int kKsTile = (kBlock / 32) * 1024;           // positions per block iteration
 constexpr int kKsSmem = kKsTile * (8 + 2 + 2);          // keys, local positions, ranks
+// Key-range shard (multi-GPU): only the suffixes whose key falls into histogram bins [bin0, bin0 + span) are counted /
+// generated; span == 0 means "everything".  A filtered suffix (key ~0) belongs to no shard.
+struct KeyRange {
+    uint32_t bin0, span;
+    __device__ __forceinline__ bool take(uint64_t key) const {
+        return span == 0 || (key != ~0ull && ((uint32_t)(key >> (64 - kShardHistBits)) - bin0) < span);
+    }
+};
 
 __global__ void __launch_bounds__(kBlock) fast2_first_digit_hist_kernel(KeySpec ks, uint64_t n, int filter,
                                                                         uint64_t chunk_elems, int shift,
-                                                                        uint32_t* __restrict__ counts) {
+                                                                        uint32_t* __restrict__ counts, KeyRange range,
+                                                                        unsigned long long* __restrict__ total) {
     constexpr int WARPS = kBlock / 32;
     __shared__ uint32_t hist[WARPS][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(kBlock) fast2_first_digit_hist_kernel(KeySpec 
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             const uint64_t key = fast2_lane_key(ks, L, j, n, filter);
-            if (L.P0 + j < end) atomicAdd(&hist[warp][(uint32_t)(key >> shift) & 255u], 1u);
+            if (L.P0 + j < end && range.take(key)) atomicAdd(&hist[warp][(uint32_t)(key >> shift) & 255u], 1u);
         }
     }
     __syncthreads();
@@ -99,13 +108,18 @@ __global__ void __launch_bounds__(kBlock) fast2_first_digit_hist_kernel(KeySpec 
 #pragma unroll
     for (int w2 = 0; w2 < WARPS; w2++) acc += hist[w2][threadIdx.x];
     counts[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x] = acc;
+    if (total) {  // number of records of this shard (the caller sizes the record arrays with it)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0 && acc) atomicAdd(total, (unsigned long long)acc);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock, 2) fast2_keygen_scatter_kernel(KeySpec ks, uint64_t n, int filter,
                                                                          uint64_t* __restrict__ keys_out,
                                                                          pos_t* __restrict__ pos_out,
                                                                          uint64_t chunk_elems, int shift,
-                                                                         const uint32_t* __restrict__ bases) {
+                                                                         const uint32_t* __restrict__ bases, KeyRange range) {
     constexpr int WARPS = kBlock / 32;
     extern __shared__ __align__(16) unsigned char ks_smem[];
     uint64_t* exk = reinterpret_cast<uint64_t*>(ks_smem);                  // records in digit order
@@ -121,7 +135,6 @@ __global__ void __launch_bounds__(kBlock, 2) fast2_keygen_scatter_kernel(KeySpec
     const uint64_t end = begin + chunk_elems < n ? begin + chunk_elems : n;
     Fast2LaneRaw raw = fast2_lane_issue(ks, begin + (uint64_t)warp * 1024, lane);
     for (uint64_t tile0 = begin; tile0 < end; tile0 += kKsTile) {
-        const uint32_t count = (end - tile0) < (uint64_t)kKsTile ? (uint32_t)(end - tile0) : (uint32_t)kKsTile;
         cnt[tid] = 0;
         __syncthreads();
         const Fast2Lane L = fast2_lane_finish(ks, raw, tile0 + (uint64_t)warp * 1024, lane, filter);
@@ -132,7 +145,8 @@ __global__ void __launch_bounds__(kBlock, 2) fast2_keygen_scatter_kernel(KeySpec
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             const uint64_t key = fast2_lane_key(ks, L, j, n, filter);
-            if (L.P0 + j < end) rkw[j * 32 + lane] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key >> shift) & 255u], 1u);
+            if (L.P0 + j < end && range.take(key))
+                rkw[j * 32 + lane] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key >> shift) & 255u], 1u);
         }
         __syncthreads();
         // thread tid owns digit tid: exclusive scan over the digits
@@ -149,6 +163,9 @@ __global__ void __launch_bounds__(kBlock, 2) fast2_keygen_scatter_kernel(KeySpec
 #pragma unroll
         for (int w2 = 0; w2 < WARPS; w2++)
             if (w2 < warp) wprefix += warp_tot[w2];
+        uint32_t count = 0;  // records of this tile (all its positions, or those inside the shard's key range)
+#pragma unroll
+        for (int w2 = 0; w2 < WARPS; w2++) count += warp_tot[w2];
         const uint32_t start = wprefix + incl - c;
         cnt[tid] = start;
         goff[tid] = running[tid] - start;
@@ -159,6 +176,7 @@ __global__ void __launch_bounds__(kBlock, 2) fast2_keygen_scatter_kernel(KeySpec
         for (int j = 0; j < 32; j++) {
             if (L.P0 + j < end) {
                 const uint64_t key = fast2_lane_key(ks, L, j, n, filter);
+                if (!range.take(key)) continue;
                 const uint32_t slot = cnt[(uint32_t)(key >> shift) & 255u] + rkw[j * 32 + lane];
                 exk[slot] = key;
                 exl[slot] = (uint16_t)(warp * 1024 + lane * 32 + j);

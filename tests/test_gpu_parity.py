@@ -591,6 +591,34 @@ def test_fast2_deep_repeats_and_shards(S):
         assert np.array_equal(np.concatenate([s.lcp for s in shards]), want.lcp)
 
 
+@pytest.mark.parametrize("fuse", ["1", "0"])
+@pytest.mark.parametrize("kw", [dict(is_dna=True), dict(is_dna=True, allow_ambiguity=True), dict()],
+                         ids=["filtered", "ambiguity", "bytes"])
+def test_shard_selection_fused_with_first_radix_pass(S, monkeypatch, fuse, kw):
+    """Key-range shards select their records and sort them in four passes; the variant that generates them already in
+    first-digit order (selection fused with key generation and the first radix pass, SUFR_B200_DEBUG_SHARD_FUSE=1:
+    measured, not the default) must give the same arrays.  Both ways for 2, 3, 8 and 33 shards (some of them empty)."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    monkeypatch.setenv("SUFR_B200_DEBUG_SHARD_FUSE", fuse)
+    rng = random.Random(len(kw) + int(fuse))
+    text = dna_with_rare(rng, 90000) + b"ACGT" * 300 + rand_text(rng, 20000, b"ACGT", repeat_p=0.05, max_rep=200)[:-1] + b"$"
+    want = O.oracle_build(text, threads=4, **kw)
+    for world in (2, 3, 8, 33):
+        shards = [S.build(S.SufrBuilderArgs(text=text, **kw), rank=r, world_size=world) for r in range(world)]
+        meta = [(s.num_suffixes, s.first_suffix, s.last_suffix) for s in shards]
+        offs, total = shard_layout(meta)
+        assert total == want.num_suffixes
+        for r, sh in enumerate(shards):
+            sh.set_shard_layout(offs[r], total)
+            prev = previous_last_suffix(meta, r)
+            if prev is not None and sh.num_suffixes:
+                sh.patch_seam(prev)
+        assert np.array_equal(np.concatenate([sh.sa for sh in shards]), want.sa)
+        assert np.array_equal(np.concatenate([sh.lcp for sh in shards]), want.lcp)
+        for sh in shards:
+            sh.free()
+
+
 def test_sharded_build_writes_one_file(S, tmp_path):
     """Every rank pwrites its slice into the same `.sufr` (sufr_b200_write, sharded): byte-identical to the
     single-process file."""
