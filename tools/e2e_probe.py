@@ -31,6 +31,8 @@ bargs = S.SufrBuilderArgs(text=memoryview(h_text.numpy()), is_dna=True, sequence
 settings = [("default", {}), ("4 widening threads", {"SUFR_B200_WIDEN_THREADS": "4"}),
             ("8 widening threads", {"SUFR_B200_WIDEN_THREADS": "8"}),
             ("plain u64 transfer", {"SUFR_B200_DEBUG_NO_COMPACT_D2H": "1"})]
+if len(sys.argv) > 2 and sys.argv[2] == "default":  # e.g. to compare SUFR_B200_DEBUG_NO_AVX512=1 between two runs
+    settings = settings[:1]
 for bits in (64, 32):
     for name, env in settings:
         for k, v in env.items():
