@@ -658,9 +658,10 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
                     wide_ok_ = true;
                 }
             }
-            round0_fast2_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), pos_spare_.get(), r0n,
-                                                                      d_lcp.get(), act_slot.get(), act_pos.get(), d_cnt.get(),
-                                                                      capacity, wide_sa_.get(), wide_lcp_.get(), deep_marks);
+            auto round0 = deep_marks ? round0_fast2_kernel<true> : round0_fast2_kernel<false>;
+            round0<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), pos_spare_.get(), r0n, d_lcp.get(),
+                                                         act_slot.get(), act_pos.get(), d_cnt.get(), capacity, wide_sa_.get(),
+                                                         wide_lcp_.get());
         } else {
             resolve0_append_kernel<<<grid_for(r0n, 4), kBlock, 0, st()>>>(keys_sorted.get(), d_sa.get(), r0n, ks, final_word,
                                                                          sort_kmask_, d_lcp.get(), act_slot.get(), act_pos.get(),

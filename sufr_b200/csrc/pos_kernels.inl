@@ -638,6 +638,7 @@ __device__ __forceinline__ RunExtent run_extent(const uint32_t* hbm, uint32_t a)
     e.pback = (L << 1) ? (uint32_t)__clz((int)(L << 1)) : 31u;
     return e;
 }
+template <bool kDeepMarks>  // a compile-time switch: the marking code costs the hot path 2 % even when it never runs
 __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __restrict__ keys,
                                                               const pos_t* __restrict__ pos,
                                                               pos_t* __restrict__ pos_out,
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
                                                               unsigned long long* __restrict__ act_count,
                                                               uint64_t capacity,
                                                               unsigned long long* __restrict__ sa64,
-                                                              unsigned long long* __restrict__ lcp64, int deep_marks) {
+                                                              unsigned long long* __restrict__ lcp64) {
     constexpr uint32_t RL = kFast2SmallGroup + 1;  // a run of RL records or more is "large"
     __shared__ uint64_t ka[kR0N], kb[kR0N];
     __shared__ pos_t pa[kR0N], pb[kR0N];
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kBlock) round0_fast2_kernel(const uint64_t* __
                     }
                     if (!head) {
                         out = kLcpPending;
-                        if (deep_marks) {  // no member of the group (equal canonical keys inside this small run) has fill
+                        if (kDeepMarks) {  // no member of the group (equal canonical keys inside this small run) has fill
                             uint64_t any = 0;
                             for (uint32_t b = h; b <= d + fwd; b++) any |= ((kb[b] & ~3ull) == c0) ? kb[b] : 0ull;
                             if (!(any & 1ull)) out = kLcpPendingDeep;
