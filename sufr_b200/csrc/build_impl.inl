@@ -895,6 +895,11 @@ void Build::doubling(DevBuf<uint32_t>& slot, DevBuf<pos_t>& pos, DevBuf<uint32_t
     const bool log_rounds = getenv("SUFR_B200_LOG_ROUNDS") != nullptr;
     while (m > 0) {
         if (doubling_rounds > 64) throw Error(SUFR_B200_ERR_INTERNAL, "prefix doubling did not converge");
+        // The working LCP array is 32 bits wide with bit 31 and the two top values reserved (common.cuh): a group that is
+        // still unresolved at h >= 2^30 can have an LCP of 2^31 or more.  Refuse rather than mis-encode.
+        if (h >= (1ull << 30))
+            throw Error(SUFR_B200_ERR_UNSUPPORTED, "suffixes that share 2^30 symbols or more: longest common prefixes of 2^31 "
+                                                   "and above do not fit the 32-bit working LCP array");
         doubling_rounds++;
         doubling_depth_ = h;
         if (log_rounds) {
