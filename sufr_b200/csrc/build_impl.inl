@@ -794,6 +794,40 @@ void Build::refine(DevBuf<uint64_t>& keys_sorted) {
             m = m2;
             nseg = nseg2;
             if (m == 0) return;
+            // ... and the larger ones, one block per group (finish_large_groups_kernel)
+            if (!getenv("SUFR_B200_DEBUG_NO_BLOCK_TAIL")) {
+                auto starts = dalloc<uint64_t>(nseg);
+                const uint32_t heads = scan_total(m, SegHeadIn{seg.get()}, scan::SumU32{}, IndexOut{starts.get()});
+                if (heads != nseg) throw Error(SUFR_B200_ERR_INTERNAL, "group count mismatch in the direct-comparison tail");
+                SUFR_CUDA_CHECK(cudaMemsetAsync(is_large.get(), 0, nseg, st()));
+                SUFR_CUDA_CHECK(cudaMemsetAsync(d_left.get(), 0, 8, st()));
+                const uint32_t blocks = (uint32_t)std::min<uint64_t>(nseg, (uint64_t)num_sms() * 16);
+                finish_large_groups_kernel<<<blocks, kBlock, 0, st()>>>(ks, m, (uint64_t)(word + 1) * K, starts.get(), nseg, seg.get(),
+                                                                       slot.get(), pos.get(), d_sa.get(), d_lcp.get(), is_large.get(),
+                                                                       d_left.get());
+                SUFR_KERNEL_CHECK();
+                launched();
+                SUFR_CUDA_CHECK(cudaMemcpyAsync(&left, d_left.get(), 8, cudaMemcpyDeviceToHost, st()));
+                SUFR_CUDA_CHECK(cudaStreamSynchronize(st()));
+                if (left == 0) return;
+                if (left < m) {  // keep what the blocks did not finish
+                    DevBuf<unsigned long long> part3;
+                    LargeIn lin3{seg.get(), is_large.get()};
+                    const unsigned long long lt3 = scan_begin(m, lin3, scan::SumU64{}, part3);
+                    const uint64_t m3 = (uint32_t)lt3, nseg3 = lt3 >> 32;
+                    auto slot3 = dalloc<uint32_t>(m3);
+                    auto pos3 = dalloc<pos_t>(m3);
+                    auto seg3 = dalloc<uint32_t>(m3);
+                    scan_finish(m, lin3, scan::SumU64{}, LeftoverOut{slot.get(), pos.get(), slot3.get(), pos3.get(), seg3.get(), seg.get()},
+                                part3);
+                    slot = std::move(slot3);
+                    pos = std::move(pos3);
+                    seg = std::move(seg3);
+                    m = m3;
+                    nseg = nseg3;
+                    if (m == 0) return;
+                }
+            }
         }
         word++;
         refine_rounds++;

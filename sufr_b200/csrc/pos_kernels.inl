@@ -1094,6 +1094,91 @@ __global__ void __launch_bounds__(kBlock) finish_small_groups_kernel(KeySpec ks,
         }
     }
 }
+// The larger groups of the same deep tail: ONE BLOCK per group orders up to kFinishCap members in shared memory with a
+// bitonic network whose comparator is the direct suffix comparison, then writes the final order and the exact LCP of
+// every new boundary.  A shard cannot run prefix doubling, and the families of a repetitive genome (hundreds of copies of
+// a segment) otherwise take one launch-bound word round per 21 symbols of their depth -- ~190 rounds on BASELINE's
+// repetitive variant.  The comparisons of a group are budgeted (kFinishBudget key-word loads): a group that exceeds it
+// (a tandem array: thousands of members that share 10^5 symbols) is left as it was, flagged for the word rounds / the
+// full-sort fallback, and so is a group with more than kFinishCap members.
+constexpr uint32_t kFinishCap = 32768 / sizeof(pos_t);
+constexpr unsigned long long kFinishBudget = 1ull << 25;
+struct SegHeadIn {
+    static constexpr bool kFlags = true;  // scan.cuh: scanned with warp votes
+    const uint32_t* seg;
+    __device__ uint32_t operator()(uint64_t a) const { return (a == 0 || seg[a] != seg[a - 1]) ? 1u : 0u; }
+};
+__global__ void __launch_bounds__(kBlock) finish_large_groups_kernel(KeySpec ks, uint64_t m, uint64_t depth,
+                                                                     const uint64_t* __restrict__ group_start,
+                                                                     uint64_t num_groups, const uint32_t* __restrict__ seg,
+                                                                     const uint32_t* __restrict__ slot,
+                                                                     const pos_t* __restrict__ pos, pos_t* __restrict__ sa,
+                                                                     uint32_t* __restrict__ lcp, uint8_t* __restrict__ is_large,
+                                                                     unsigned long long* __restrict__ left_elems) {
+    __shared__ pos_t sp[kFinishCap];
+    __shared__ unsigned long long work;
+    constexpr pos_t kInf = ~(pos_t)0;  // padding up to the power of two: sorts behind every suffix
+    const uint64_t K = ks.pt.K;
+    for (uint64_t g = blockIdx.x; g < num_groups; g += gridDim.x) {
+        const uint64_t a0 = group_start[g];
+        const uint64_t len = (g + 1 < num_groups ? group_start[g + 1] : m) - a0;
+        __syncthreads();  // the previous group's shared memory is no longer read
+        if (len > kFinishCap) {
+            if (threadIdx.x == 0) {
+                is_large[seg[a0] & ~kSegDeep] = 1;
+                atomicAdd(left_elems, (unsigned long long)len);
+            }
+            continue;
+        }
+        uint32_t n2 = 2;
+        while (n2 < len) n2 <<= 1;
+        for (uint32_t i = threadIdx.x; i < n2; i += kBlock) sp[i] = i < len ? pos[a0 + i] : kInf;
+        if (threadIdx.x == 0) work = 0;
+        __syncthreads();
+        bool over = false;
+        for (uint32_t k = 2; k <= n2 && !over; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long mine = 0;
+                for (uint32_t t = threadIdx.x; t < n2 / 2; t += kBlock) {
+                    const uint32_t i = 2 * t - (t & (j - 1)), ixj = i + j;
+                    const pos_t x = sp[i], y = sp[ixj];
+                    bool y_less = false;  // y < x ?
+                    if (y != kInf) {
+                        if (x == kInf) y_less = true;
+                        else {
+                            uint64_t l;
+                            y_less = suffix_less(ks, y, x, depth, l);
+                            mine += (l - depth) / K + 1;
+                        }
+                    }
+                    const bool ascending = (i & k) == 0;
+                    if (y_less == ascending) { sp[i] = y; sp[ixj] = x; }
+                }
+                if (mine) atomicAdd(&work, mine);
+                __syncthreads();
+                over = work > kFinishBudget;
+                __syncthreads();
+                if (over) break;
+            }
+        }
+        if (over) {  // nothing has been written: the group stays as it was
+            if (threadIdx.x == 0) {
+                is_large[seg[a0] & ~kSegDeep] = 1;
+                atomicAdd(left_elems, (unsigned long long)len);
+            }
+            continue;
+        }
+        for (uint32_t i = threadIdx.x; i < len; i += kBlock) {
+            const pos_t p = sp[i];
+            sa[slot[a0 + i]] = p;
+            if (i > 0) {  // the head keeps the LCP of an earlier round
+                uint64_t l;
+                suffix_less(ks, sp[i - 1], p, depth, l);
+                lcp[slot[a0 + i]] = (uint32_t)l;
+            }
+        }
+    }
+}
 // the members of the groups finish_small_groups_kernel left over, with new group numbers
 struct LeftoverOut {
     const uint32_t* slot;

@@ -619,6 +619,59 @@ def test_shard_selection_fused_with_first_radix_pass(S, monkeypatch, fuse, kw):
             sh.free()
 
 
+def family_text(rng, n, seg_len=2000, copies=30, mut=0.01):
+    """Random DNA with one segment copied `copies` times, each copy with ~1 % substitutions: suffix groups of up to
+    `copies` members whose common prefixes run to hundreds of bases (a repeat family of a genome)."""
+    acgt = b"ACGT"
+    seg = bytes(rng.choice(acgt) for _ in range(seg_len))
+    out = bytearray()
+    per = (n - copies * seg_len) // copies
+    nrng = np.random.default_rng(rng.randrange(1 << 30))
+    for _ in range(copies):
+        out += np.frombuffer(acgt, dtype=np.uint8)[nrng.integers(0, 4, per)].tobytes()
+        c = bytearray(seg)
+        for i in range(seg_len):
+            if rng.random() < mut:
+                c[i] = rng.choice(acgt)
+        out += c
+    return bytes(out) + b"$"
+
+
+@pytest.mark.parametrize("block_tail", [True, False])
+def test_repeat_families_finish_by_direct_comparison(S, monkeypatch, block_tail):
+    """Subset attempts (shards, pre-filtered builds) cannot run prefix doubling: the deep tail -- pairs and small groups
+    by one thread each, families of up to 8192 members by one block each (bitonic network over direct suffix
+    comparisons) -- is finished in one step instead of one word round per 21 bases."""
+    from sufr_b200.distributed import previous_last_suffix, shard_layout
+    if not block_tail:
+        monkeypatch.setenv("SUFR_B200_DEBUG_NO_BLOCK_TAIL", "1")
+    rng = random.Random(77)
+    text = family_text(rng, 4_000_000)   # the family is 1.5 % of the text: the tail starts right after the third word
+    want = O.oracle_build(text, is_dna=True, threads=4)
+    rounds = []
+    for world in (1, 2, 3):
+        shards = [S.build(S.SufrBuilderArgs(text=text, is_dna=True), rank=r, world_size=world) for r in range(world)]
+        if world > 1:
+            assert all(sh.c.doubling_rounds == 0 for sh in shards)
+            rounds.append(max(sh.c.refine_rounds for sh in shards))
+        meta = [(sh.num_suffixes, sh.first_suffix, sh.last_suffix) for sh in shards]
+        offs, total = shard_layout(meta)
+        assert total == want.num_suffixes
+        for r, sh in enumerate(shards):
+            sh.set_shard_layout(offs[r], total)
+            prev = previous_last_suffix(meta, r)
+            if prev is not None and sh.num_suffixes:
+                sh.patch_seam(prev)
+        assert np.array_equal(np.concatenate([sh.sa for sh in shards]), want.sa)
+        assert np.array_equal(np.concatenate([sh.lcp for sh in shards]), want.lcp)
+        for sh in shards:
+            sh.free()
+    if block_tail:
+        assert max(rounds) <= 8, rounds      # the tail starts after the third word
+    else:
+        assert max(rounds) >= 12, rounds     # one round per key word until the families have split up otherwise
+
+
 def test_sharded_build_writes_one_file(S, tmp_path):
     """Every rank pwrites its slice into the same `.sufr` (sufr_b200_write, sharded): byte-identical to the
     single-process file."""

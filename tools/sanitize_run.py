@@ -48,6 +48,20 @@ def tandem(seed, n):
     return np.concatenate(parts)[:n].tobytes() + b"A$"
 
 
+def family(seed, n, seg_len=160, copies=12):
+    """one segment copied `copies` times with a substitution or two each, in random DNA (3 % of the text)"""
+    rng = random.Random(seed)
+    seg = bytes(rng.choice(b"ACGT") for _ in range(seg_len))
+    per = (n - copies * seg_len) // copies
+    out = bytearray()
+    for _ in range(copies):
+        out += bytes(rng.choice(b"ACGT") for _ in range(per))
+        c = bytearray(seg)
+        c[rng.randrange(seg_len // 2, seg_len)] = rng.choice(b"ACGT")
+        out += c
+    return bytes(out) + b"$"
+
+
 def main():
     n = int(os.environ.get("SANITIZE_N", "40000"))
     cases = [
@@ -63,6 +77,7 @@ def main():
         ("dense round 0", rand_text(9, n, b"ACGT", 0.05), dict(is_dna=True), 32, {"SUFR_B200_DEBUG_SPARSE_CAP": "16"}),
         ("deep repeats, inverse suffix array by sorting", tandem(10, n), dict(is_dna=True, allow_ambiguity=True), 32,
          {"SUFR_B200_DEBUG_SORT_ISA": "1"}),
+        ("repeat family: shards finish by direct comparison (one block per group)", family(11, 2 * n), dict(is_dna=True), 32, {}),
     ]
     for name, text, kw, bits, env in cases:
         for k, v in env.items():
