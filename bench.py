@@ -560,6 +560,8 @@ def run_e2e_file(args, S, ctx, d_text, text_len, bargs, total_suffixes, dev):
         return {"value": res["num_suffixes"] / dt, "unit": "suffixes/s", "s": dt, "file_bytes": size, "path": "/dev/shm",
                 "device_ms": res["timings"]["total_ms"], "write_ms": res["timings"].get("d2h_ms"),
                 "note": "host text -> sufr_b200_create_multi on this GPU -> .sufr (version 6) on a RAM disk, one run, wall clock"}
+    except Exception as e:  # an extra figure must not cost the bench line (e.g. a RAM disk that fills up)
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
     finally:
         try:
             os.remove(path)
