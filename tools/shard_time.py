@@ -1,5 +1,10 @@
+#!/usr/bin/env python
+"""Device time of single key-range shards of a BASELINE config, emulated on ONE GPU (rank r of N builds only its key
+range): usage: tools/shard_time.py <scale> <world>, e.g. `tools/shard_time.py 1.0 8` for shards 1 and 7 of 8 of config 2b."""
 import sys, time, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools"))
 import torch, bench, sufr_b200 as S, workloads
 w = workloads.ALL["config2b"](int(bench.FULL_SIZES["config2b"] * float(sys.argv[1])))
 t = torch.frombuffer(bytearray(w.text), dtype=torch.uint8).cuda()
